@@ -1,0 +1,91 @@
+"""Shared parity-test plumbing: drive the CUDA engine and the CPU oracle in
+lock-step on the same inputs and compare every observable bit-for-bit."""
+import numpy as np
+
+from oracle.oracle import Oracle, PARITY_THRESHOLD
+from oracle.ref_harness import dispatch_decision
+
+
+def make_oracle(city, V, minute, pickup, delivery, period=10, threshold=PARITY_THRESHOLD):
+    return Oracle(city.cost_u8, city.node2cluster.astype(np.int32), city.nb_off.astype(np.int32),
+                  city.nb_idx.astype(np.int32), minute, pickup, delivery, V, period,
+                  city.depth_limit, city.neighbor_can_server, threshold)
+
+
+def random_orders(city, n, rng, n_minutes=200, hot=0.6):
+    """Sorted synthetic order stream with hot spots (ties + contention)."""
+    valid = city.valid_nodes().astype(np.int32)
+    minute = np.sort(rng.integers(0, n_minutes, n)).astype(np.int32)
+    hotset = rng.choice(valid, size=max(1, len(valid) // 20), replace=False)
+    pick = np.where(rng.random(n) < hot, rng.choice(hotset, n), rng.choice(valid, n)).astype(np.int32)
+    drop = np.where(rng.random(n) < hot, rng.choice(hotset, n), rng.choice(valid, n)).astype(np.int32)
+    return minute, pick, drop
+
+
+def policy_moves(oracle, city, tick):
+    """The shared deterministic dispatch policy (oracle/ref_harness.py),
+    evaluated on the oracle's idle lists: cluster-ID order, list order."""
+    veh, node = [], []
+    for c in range(city.n_clusters):
+        nb = [int(x) for x in city.neighbors(c) if len(city.cluster_nodes[int(x)])]
+        for v in oracle.idle_list(c):
+            k = dispatch_decision(tick, int(v), len(nb))
+            if k < 0:
+                continue
+            nodes = city.cluster_nodes[nb[k]]
+            veh.append(int(v))
+            node.append(int(nodes[(tick + int(v)) % len(nodes)]))
+    return np.array(veh, np.int32), np.array(node, np.int32)
+
+
+def lockstep(engine, oracles, loc0, dispatch=False, check_lists_every=1, ticks=None):
+    """oracles: one per replica.  Returns the number of ticks compared."""
+    city = engine.city
+    R = engine.R
+    engine.reset(loc0)
+    for r, o in enumerate(oracles):
+        o.reset(loc0 if np.ndim(loc0) == 1 else loc0[r])
+    T = engine.T if ticks is None else ticks
+    for k in range(T):
+        assert not oracles[0].done()
+        engine.update(k)
+        for o in oracles:
+            o.update()
+        if check_lists_every and k % check_lists_every == 0:
+            for r in (0, R - 1):
+                got = engine.idle_lists(r)
+                exp = oracles[r].idle_lists()
+                for c in range(city.n_clusters):
+                    assert np.array_equal(got[c], exp[c]), f"idle list order tick {k} replica {r} cluster {c}"
+        engine.match(k)
+        engine.supply_expect(k)
+        for o in oracles:
+            o.match(); o.supply_expect(); o.snapshot_pre_dispatch()
+        t = {n: engine.tensors[n].cpu().numpy() for n in ("per_match", "per_dispatch", "supply", "n_orders", "idle_live")}
+        for r, o in enumerate(oracles):
+            assert np.array_equal(t["per_match"][r], o.per_match()), f"per_match tick {k} replica {r}"
+            assert np.array_equal(t["n_orders"][r], o.n_orders()), f"n_orders tick {k} replica {r}"
+            assert np.array_equal(t["per_dispatch"][r], o.per_dispatch()), f"per_dispatch tick {k} replica {r}"
+            assert np.array_equal(t["supply"][r], o.supply()), f"supply tick {k} replica {r}"
+        if dispatch:
+            off, mv, mn = [0], [], []
+            for r, o in enumerate(oracles):
+                v, n = policy_moves(o, city, k)
+                assert o.dispatch(v, n) == len(v)
+                mv.append(v); mn.append(n); off.append(off[-1] + len(v))
+            engine.dispatch(k, np.array(off, np.int32), np.concatenate(mv), np.concatenate(mn))
+        for o in oracles:
+            o.end_tick()
+        later = engine.tensors["idle_live"].cpu().numpy()
+        for r, o in enumerate(oracles):
+            assert np.array_equal(later[r], o.later_dispatch()), f"later_dispatch tick {k} replica {r}"
+    if ticks is None:
+        assert oracles[0].done()
+    st = engine.stats().cpu().numpy()
+    for r, o in enumerate(oracles):
+        veh, wait, delta = engine.order_results(r)
+        assert np.array_equal(veh, o.order_vehicle()), f"matched vehicle ids replica {r}"
+        assert np.array_equal(wait, o.order_wait()), f"wait replica {r}"
+        os_ = o.stats()
+        assert tuple(st[r][:9]) == tuple(os_[:9]), f"stats replica {r}: {st[r]} vs {os_}"
+    return T
