@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/sec of the batched dispatch hot path on B200.
+
+One "step" = one full-day rollout (T=148 time slots: Update -> order advance ->
+match/reject -> SupplyExpect -> snapshots) of ALL replicas on this GPU, i.e.
+R*T env-steps.  Workload = BASELINE.json configs[1] by default:
+1024 replicas x 192-grid x 2000 vehicles, synthetic Didi-rate orders
+(~200k orders/day/replica, Philox streams generated on device).
+
+  value     env-steps/s with inputs resident in HBM (device-timed, CUDA events)
+  e2e       the same through the public engine API with HOST inputs: every step
+            copies the step's order streams + tick offsets + vehicle placement
+            from pinned host memory and reads the episode returns back
+  roofline  match kernel: algorithmic bytes / measured launch time / measured HBM peak
+  cpu_baseline  the C oracle (port of the reference loop) on all host cores,
+            bounded sample of the same workload (rank 0, N=1 only)
+
+--impl reference times the reference's CPU implementation of the path (the C
+port in oracle/ -- the Python reference itself cannot travel to the GPU box) on
+all host cores and prints the same JSON line with "impl": "reference".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (replicas/GPU, side_m, service_m, neighbor_can_server, vehicles)
+    "config2": dict(replicas=1024, side=800, service=800, ncs=False, vehicles=2000,
+                    desc="1024 replicas x 192-grid x 2000 vehicles, synthetic Didi-rate orders, depth 0"),
+    "config3": dict(replicas=4096, side=800, service=2800, ncs=True, vehicles=5000,
+                    desc="4096 replicas x 192-grid x 5000 vehicles, neighbour-search depth 3"),
+    "config5": dict(replicas=2048, side=400, service=400, ncs=False, vehicles=10000,
+                    desc="2048 replicas/GPU x 768-grid x 10000 vehicles, depth 0"),
+}
+SEED = 1234
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_workload(w, replicas, device, first_replica):
+    from vehicles_dispatch_simulator_b200.engine import DispatchEngine
+    from vehicles_dispatch_simulator_b200.synthetic import DemandTables, synthetic_grid_city
+    city = synthetic_grid_city(side_m=w["side"], service_m=w["service"], neighbor_can_server=w["ncs"])
+    tables = DemandTables(city)
+    eng = DispatchEngine(city, w["vehicles"], replicas=replicas, ticks=tables.ticks, max_orders=tables.max_orders,
+                         per_replica_orders=True, max_orders_per_tick=tables.max_orders_per_tick, device=device)
+    eng.generate_orders(tables, seed=SEED, first_replica=first_replica)
+    loc0 = eng.generate_placement(seed=SEED, first_replica=first_replica)
+    return city, tables, eng, loc0
+
+
+def cpu_port_run(city, eng, loc0, tables, sample_replicas, budget_s, threads, oracles=None):
+    """Oracle (C port of the reference loop) on host threads over the first
+    `sample_replicas` replicas' streams, repeated until ~budget_s of wall."""
+    from concurrent.futures import ThreadPoolExecutor
+    from tests.helpers import engine_replica_orders, make_oracle
+    S = sample_replicas
+    locs = loc0[:S].cpu().numpy().astype(np.int32)
+    if oracles is None:
+        oracles = []
+        for r in range(S):
+            minute, pick, drop = engine_replica_orders(eng, r, tables.n_slots)
+            oracles.append(make_oracle(city, eng.V, minute, pick, drop))
+
+    def one(r):
+        oracles[r].reset(locs[r])
+        return oracles[r].run()
+
+    ticks = 0
+    t0 = time.perf_counter()
+    rounds = 0
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        while True:
+            ticks += sum(ex.map(one, range(S)))
+            rounds += 1
+            if time.perf_counter() - t0 >= budget_s:
+                break
+    wall = time.perf_counter() - t0
+    return ticks / wall, wall, rounds, oracles
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
+    ap.add_argument("--replicas", type=int, default=None, help="replicas per GPU (default: the workload's)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    w = WORKLOADS[args.workload]
+    R = args.replicas or w["replicas"]
+    cores = os.cpu_count() or 1
+
+    # ------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        torch.cuda.set_device(0)
+        S = min(R, 4 * cores)
+        city, tables, eng, loc0 = build_workload(w, S, 0, 0)
+        vals = []
+        oracles = None
+        for i in range(args.warmup + args.steps):
+            v, wall, rounds, oracles = cpu_port_run(city, eng, loc0, tables, S, 0.0, cores, oracles)
+            if i >= args.warmup:
+                vals.append((v, wall))
+        tot_ticks = sum(v * wl for v, wl in vals)
+        tot_wall = sum(wl for _, wl in vals)
+        value = tot_ticks / tot_wall
+        line = {"impl": "reference", "metric": "env-steps/sec", "value": value, "unit": "env-steps/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1e3 * tot_wall / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u8/int32", "data": "synthetic",
+                "config": {"workload": w["desc"], "replicas_sampled": S, "clusters": city.n_clusters,
+                           "vehicles": w["vehicles"], "ticks": tables.ticks,
+                           "note": "each step = one full-day episode of the sampled replicas on host threads"},
+                "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                                 "sample": f"{S} replicas x {tables.ticks} ticks per step, C port of the reference loop, {cores} threads"},
+                "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "cluster_ticks_per_sec": value * city.n_clusters}
+        print(json.dumps(line))
+        return 0
+
+    # ----------------------------------------------------------------- our arm
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from vehicles_dispatch_simulator_b200.parallel import ReplicaShard
+    shard = ReplicaShard(R, rank, world)
+    city, tables, eng, loc0 = build_workload(w, R, local_rank, shard.first_replica)
+    T = eng.T
+
+    def episode():
+        eng.reset(loc0)
+        eng.rollout(0, T)
+        st = eng.stats()
+        return shard.all_gather_returns(st)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        ret = episode()
+    barrier()
+    # ---- timed region: EXACTLY K steps, device-timed on the launching stream
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    l0 = eng.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        ret = episode()
+    ev1.record()
+    barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    launches = eng.launches - l0
+    clk = clocks.stop() if clocks else None
+    t_el = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_el, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t_el.item())
+    env_steps = world * R * T * args.steps
+    value = env_steps / (elapsed_ms * 1e-3)
+
+    # ---- e2e: host buffers in, returns out, copies inside the timed region
+    n_loc = loc0.numel() * 2
+    h_pd = torch.empty(eng.order_pd.shape, dtype=eng.order_pd.dtype, pin_memory=True)
+    h_toff = torch.empty(eng.tick_off.shape, dtype=eng.tick_off.dtype, pin_memory=True)
+    h_loc = torch.empty(loc0.shape, dtype=loc0.dtype, pin_memory=True)
+    h_ret = torch.empty((shard.total, 6), dtype=torch.int64, pin_memory=True)
+    h_pd.copy_(eng.order_pd); h_toff.copy_(eng.tick_off); h_loc.copy_(loc0)
+    d_loc = torch.empty_like(loc0)
+    h2d = h_pd.numel() * 4 + h_toff.numel() * 4 + n_loc
+    d2h = h_ret.numel() * 8
+
+    def episode_e2e():
+        eng.order_pd.copy_(h_pd, non_blocking=True)
+        eng.tick_off.copy_(h_toff, non_blocking=True)
+        d_loc.copy_(h_loc, non_blocking=True)
+        eng._compute_values()
+        eng.reset(d_loc)
+        eng.rollout(0, T)
+        out = shard.all_gather_returns(eng.stats())
+        h_ret.copy_(out, non_blocking=True)
+
+    episode_e2e()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_host0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        episode_e2e()
+    e1.record()
+    barrier()
+    e2e_ms = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t_host0))
+    t_el = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_el, op=dist.ReduceOp.MAX)
+    e2e_value = env_steps / (float(t_el.item()) * 1e-3)
+    assert torch.equal(h_ret[shard.first_replica:shard.first_replica + R], ret[shard.first_replica:shard.first_replica + R].cpu())
+
+    # ---- per-kernel device times (one instrumented episode, CUDA events on the launch stream)
+    names = ("update", "match", "supply")
+    evs = {n: [] for n in names}
+    eng.reset(loc0)
+    for k in range(T):
+        for n, fn in zip(names, (eng.update, eng.match, eng.supply_expect)):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(k); b.record()
+            evs[n].append((a, b))
+    torch.cuda.synchronize(dev)
+    kt = {n: float(sum(a.elapsed_time(b) for a, b in evs[n])) for n in names}      # ms per episode
+    st = eng.stats().cpu().numpy().astype(np.float64)
+    O, A, M, P = st[:, 0].sum(), st[:, 7].sum(), st[:, 8].sum(), st[:, 6].sum()
+    V, Cn = eng.V, eng.nC
+    # algorithmic bytes: B_step = 12V + 12(A+M) + 8O + 16C + P, split per kernel
+    bytes_k = {"update": 12.0 * V * R * T + 12 * A + 8.0 * Cn * R * T,
+               "match": 12 * M + 8 * O + P + 4.0 * Cn * R * T,
+               "supply": 4.0 * Cn * R * T}
+    b_total = sum(bytes_k.values())
+    peak, peak_src = measured_peak_gbs()
+    dom = max(names, key=lambda n: kt[n])
+    ach = bytes_k["match"] / (kt["match"] * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": "match_search_kernel" if (w["ncs"] and city.depth_limit > 0) else "match_local_kernel",
+            "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak,
+            "traffic": None,
+            "avg_launch_us": 1e3 * kt["match"] / T,
+            "algorithmic_bytes_per_launch": bytes_k["match"] / T,
+            "kernel_ms_per_episode": kt, "dominant_kernel": dom,
+            "whole_tick": {"bytes_per_env_step": b_total / (R * T),
+                           "achieved": b_total / (sum(kt.values()) * 1e-3) / 1e9,
+                           "frac": b_total / (sum(kt.values()) * 1e-3) / 1e9 / peak},
+            "per_env_step": {"O_t": O / (R * T), "A_t": A / (R * T), "M_t": M / (R * T), "P_t": P / (R * T)}}
+
+    # ---- CPU baseline + in-bench parity spot check (rank 0, N=1 only)
+    cpu = None
+    parity = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        S = min(R, 4 * cores)
+        v, wall, rounds, oracles = cpu_port_run(city, eng, loc0, tables, S, args.cpu_seconds, cores)
+        cpu = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
+               "sample": f"first {S} replicas x {T} ticks x {rounds} rounds ({wall:.1f} s), C port of the reference loop, {cores} threads"}
+        got = eng.stats().cpu().numpy()
+        parity = all(tuple(got[r][:9]) == tuple(oracles[r].stats()[:9]) for r in range(S)) and \
+            all(np.array_equal(eng.order_results(r)[0], oracles[r].order_vehicle()) for r in range(min(S, 4)))
+
+    if rank == 0:
+        line = {"metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32",
+                "data": "synthetic",
+                "config": {"workload": w["desc"], "replicas_per_gpu": R, "clusters": Cn, "vehicles": V,
+                           "ticks": T, "orders_per_day_mean": tables.mean_total, "search_depth": city.depth_limit,
+                           "step": "one full-day rollout of all replicas (R*T env-steps)",
+                           "l2": "inputs larger than L2 (order streams + results %.2f GB per step); no explicit flush"
+                                 % ((eng.order_pd.numel() * 8) / 1e9)},
+                "cluster_ticks_per_sec": value * Cn,
+                "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+                "parity_check_vs_oracle": parity}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

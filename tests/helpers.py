@@ -89,3 +89,16 @@ def lockstep(engine, oracles, loc0, dispatch=False, check_lists_every=1, ticks=N
         os_ = o.stats()
         assert tuple(st[r][:9]) == tuple(os_[:9]), f"stats replica {r}: {st[r]} vs {os_}"
     return T
+
+
+def engine_replica_orders(eng, r, n_slots):
+    """(minute, pickup, delivery) of replica r's device-resident order stream
+    (synthetic streams: slot s == tick s+1 == minute 10*s)."""
+    ro = 0 if eng.OR == 1 else r
+    n = int(eng.n_orders_total[ro].item())
+    pd = eng.order_pd[ro, :n].cpu().numpy().astype(np.uint32)
+    toff = eng.tick_off[ro].cpu().numpy()
+    tick = np.searchsorted(toff, np.arange(n), side="right") - 1
+    tick = np.clip(tick, 1, n_slots)
+    minute = (10 * (tick - 1)).astype(np.int32)
+    return minute, (pd & 0xFFFF).astype(np.int32), (pd >> 16).astype(np.int32)
