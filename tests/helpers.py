@@ -102,3 +102,109 @@ def engine_replica_orders(eng, r, n_slots):
     tick = np.clip(tick, 1, n_slots)
     minute = (10 * (tick - 1)).astype(np.int32)
     return minute, (pd & 0xFFFF).astype(np.int32), (pd >> 16).astype(np.int32)
+
+
+# ------------------------------------------------------------ golden fixtures
+import os as _os
+
+GOLDEN = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden")
+SMALL_CASES = ("grid_d0", "grid_d2", "kmeans_d1", "grid_d0_dispatch", "grid_d1_dispatch")
+REAL_CASES = ("kmeans", "grid6000", "grid5000d3")
+
+
+def load_golden(name, real=False):
+    """inputs + traces recorded from the unmodified reference (make_golden.py)."""
+    if real:
+        p = _os.path.join(GOLDEN, "_real", f"real_{name}.npz")
+        if not _os.path.exists(p):
+            return None
+        z = dict(np.load(p))
+        z["in_cost_u8"] = np.load(_os.path.join(GOLDEN, "_real", "real_cost.npz"))["cost_u8"]
+        return z
+    return dict(np.load(_os.path.join(GOLDEN, f"small_{name}.npz")))
+
+
+def golden_city(z):
+    from vehicles_dispatch_simulator_b200.engine import City
+    p, depth, ncs, C, V, disp = [int(x) for x in z["in_params"]]
+    nodes = [z["in_cl_nodes"][z["in_cl_nodes_off"][c]:z["in_cl_nodes_off"][c + 1]] for c in range(C)]
+    return City(z["in_cost_u8"], z["in_node2cluster"], z["in_nb_off"], z["in_nb_idx"], depth_limit=depth,
+                neighbor_can_server=bool(ncs), cluster_nodes=nodes), V, p
+
+
+def golden_idle_lists(z, k, C):
+    off, flat = z["tr_idle_off"], z["tr_idle_flat"]
+    return [flat[off[k * C + c]:off[k * C + c + 1]] for c in range(C)]
+
+
+def check_oracle_against_golden(z):
+    """CPU oracle vs the reference's recorded trace, every observable."""
+    city, V, p = golden_city(z)
+    C = city.n_clusters
+    o = make_oracle(city, V, z["in_order_minute"], z["in_order_pickup"], z["in_order_delivery"], p)
+    o.reset(z["in_veh_loc0"])
+    mo, mv = z["tr_moves_off"], z["tr_moves"]
+    k = 0
+    while not o.done():
+        o.update()
+        exp = golden_idle_lists(z, k, C)
+        for c in range(C):
+            assert np.array_equal(o.idle_list(c), exp[c]), f"idle list order tick {k} cluster {c}"
+        o.match()
+        assert np.array_equal(o.per_match(), z["tr_per_match"][k])
+        assert np.array_equal(o.n_orders(), z["tr_n_orders"][k])
+        o.supply_expect(); o.snapshot_pre_dispatch()
+        assert np.array_equal(o.supply(), z["tr_supply"][k]), f"supply tick {k}"
+        assert np.array_equal(o.per_dispatch(), z["tr_per_dispatch"][k])
+        m = mv[mo[k]:mo[k + 1]]
+        if len(m):
+            assert o.dispatch(m[:, 0], m[:, 1]) == len(m)
+        o.end_tick()
+        assert np.array_equal(o.later_dispatch(), z["tr_later_dispatch"][k])
+        assert tuple(o.stats()[:3]) == tuple(z["tr_counters"][k])
+        k += 1
+    assert k == int(z["tr_final"][6])
+    assert np.array_equal(o.order_vehicle(), z["tr_order_vehicle"])
+    assert np.array_equal(o.order_wait(), z["tr_order_wait"])
+    assert tuple(o.stats()[:6]) == tuple(z["tr_final"][:6])
+    return k
+
+
+def check_engine_against_golden(engine, z, replicas=(0,), lists_every=1):
+    """CUDA engine (already bound to the golden inputs) vs the reference's trace."""
+    city = engine.city
+    C = city.n_clusters
+    T = int(z["tr_final"][6])
+    assert engine.T == T
+    engine.reset(z["in_veh_loc0"])
+    mo, mv = z["tr_moves_off"], z["tr_moves"]
+    for k in range(T):
+        engine.update(k)
+        if lists_every and k % lists_every == 0:
+            exp = golden_idle_lists(z, k, C)
+            for r in replicas:
+                got = engine.idle_lists(r)
+                for c in range(C):
+                    assert np.array_equal(got[c], exp[c]), f"idle list order tick {k} cluster {c}"
+        engine.match(k)
+        engine.supply_expect(k)
+        t = {n: engine.tensors[n].cpu().numpy() for n in ("per_match", "per_dispatch", "supply", "n_orders")}
+        for r in replicas:
+            assert np.array_equal(t["per_match"][r], z["tr_per_match"][k]), f"per_match tick {k}"
+            assert np.array_equal(t["n_orders"][r], z["tr_n_orders"][k]), f"n_orders tick {k}"
+            assert np.array_equal(t["supply"][r], z["tr_supply"][k]), f"supply tick {k}"
+            assert np.array_equal(t["per_dispatch"][r], z["tr_per_dispatch"][k]), f"per_dispatch tick {k}"
+        m = mv[mo[k]:mo[k + 1]]
+        if len(m):
+            off = np.arange(engine.R + 1, dtype=np.int32) * len(m)
+            engine.dispatch(k, off, np.tile(m[:, 0], engine.R), np.tile(m[:, 1], engine.R))
+        later = engine.tensors["idle_live"].cpu().numpy()
+        for r in replicas:
+            assert np.array_equal(later[r], z["tr_later_dispatch"][k]), f"later_dispatch tick {k}"
+    st = engine.stats().cpu().numpy()
+    for r in replicas:
+        veh, wait, _ = engine.order_results(r)
+        assert np.array_equal(veh, z["tr_order_vehicle"]), "matched vehicle ids"
+        assert np.array_equal(wait, z["tr_order_wait"]), "wait"
+        assert tuple(st[r][:6]) == tuple(z["tr_final"][:6]), f"{st[r]} vs {z['tr_final']}"
+    return T

@@ -1,0 +1,195 @@
+"""CPU: host-side logic (no GPU compute): C-ABI surface, packers, search lists,
+replica sharding over gloo (world_size 2), facade setup parity."""
+import ctypes
+import os
+import random
+import re
+import subprocess
+import sys
+import time
+
+import numpy as np
+import pytest
+
+from tests.helpers import GOLDEN, load_golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_c_abi_exports_every_declared_symbol():
+    from vehicles_dispatch_simulator_b200 import _native
+    hdr = open(os.path.join(ROOT, "include", "vds.h")).read()
+    declared = set(re.findall(r"\b(vds_[a-z_]+)\s*\(", hdr))
+    declared -= {"vds_handle_s"}
+    assert declared == set(_native.EXPORTS), declared ^ set(_native.EXPORTS)
+    L = _native.lib()                      # loads libvds.so (no compute, no GPU needed)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.vds_abi_version() == 1
+    assert L.vds_padded_vehicles(2001) == 2008
+    # struct layouts agree with the header's field counts
+    assert ctypes.sizeof(_native.Config) == 12 * 4 + 8
+    assert ctypes.sizeof(_native.State) == 17 * 8
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from vehicles_dispatch_simulator_b200 import VdsError
+    from vehicles_dispatch_simulator_b200.engine import DispatchEngine
+    from vehicles_dispatch_simulator_b200.synthetic import synthetic_grid_city
+    with pytest.raises(VdsError):
+        DispatchEngine(synthetic_grid_city(n_nodes=200), 10)
+
+
+def test_product_package_never_imports_oracle():
+    pkg = os.path.join(ROOT, "vehicles_dispatch_simulator_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("the oracle tests", ""), f
+
+
+def test_tick_offsets_q7_q8():
+    from vehicles_dispatch_simulator_b200.engine import tick_offsets
+    m = np.array([0, 0, 3, 9, 10, 19, 20, 1439])
+    off, T = tick_offsets(m, 10)
+    assert T == 148                                    # floor(1439/10) + 5
+    assert off[0] == 0 and off[1] == 0                 # tick 0 is empty
+    assert off[2] == 4 and off[3] == 6 and off[4] == 7
+    assert off[-1] == len(m) - 1                       # last order never consumed
+
+
+def test_search_list_is_dfs_preorder_not_bfs_ball():
+    from vehicles_dispatch_simulator_b200.synthetic import synthetic_grid_city
+    city = synthetic_grid_city(service_m=2800, neighbor_can_server=True, n_nodes=300)
+    assert city.depth_limit == 3
+    off, idx = city.search_lists()
+
+    def rec(c, deep, vis, out):                        # the reference's recursion, restated
+        if deep > 3 or c in vis:
+            return
+        vis[c] = True
+        out.append(c)
+        for j in city.neighbors(c):
+            rec(int(j), deep + 1, vis, out)
+
+    sizes = []
+    for s in range(city.n_clusters):
+        out = []
+        rec(s, 0, {}, out)
+        assert list(idx[off[s]:off[s + 1]]) == out
+        sizes.append(len(out))
+        # BFS ball of radius 3
+        ball, frontier = {s}, {s}
+        for _ in range(3):
+            frontier = {int(j) for c in frontier for j in city.neighbors(c)} - ball
+            ball |= frontier
+        assert set(out) <= ball
+    assert max(sizes) <= 21 and abs(np.mean(sizes) - 18.47) < 0.1     # SURVEY Q3 [measured]
+
+
+def test_grid_neighbor_order():
+    from vehicles_dispatch_simulator_b200.synthetic import grid_neighbors, grid_scale
+    gw, gh, depth = grid_scale((104.011, 104.125, 30.618, 30.703), 800, 800)
+    assert (gw, gh, depth) == (16, 12, 0)
+    assert grid_scale((104.011, 104.125, 30.618, 30.703), 400, 400)[:2] == (32, 24)
+    assert grid_scale((104.011, 104.125, 30.618, 30.703), 800, 2800)[2] == 3
+    off, idx = grid_neighbors(16, 12)
+    i = 16 * 5 + 7
+    assert list(idx[off[i]:off[i + 1]]) == [i + 16, i - 16, i - 1, i + 1, i + 15, i - 17, i + 17, i - 15]
+    assert list(idx[off[0]:off[1]]) == [16, 1, 17]
+
+
+@pytest.mark.parametrize("name", ["grid_d2", "kmeans_d1"])
+def test_facade_setup_matches_reference_inputs(name):
+    """CreateAllInstantiate (host packer) reproduces exactly the arrays the
+    reference built from the same CSV files: node->cluster map, neighbour
+    lists in order, post-ReadOrder order stream, OrderValue, and the
+    random.seed(0) vehicle placement."""
+    from tests.golden.make_golden import SMALL
+    from vehicles_dispatch_simulator_b200.setting import LocalRegionBound, TIMESTEP
+    from vehicles_dispatch_simulator_b200.simulation import Simulation
+    os.environ["TZ"] = "UTC"
+    time.tzset()
+    z = load_golden(name)
+    kw = dict(SMALL[name])
+    sim = Simulation(ClusterMode=kw["ClusterMode"], DemandPredictionMode="None", DispatchMode="Simulation",
+                     VehiclesNumber=kw["VehiclesNumber"], TimePeriods=TIMESTEP, LocalRegionBound=LocalRegionBound,
+                     SideLengthMeter=800, VehiclesServiceMeter=kw.get("VehiclesServiceMeter", 800),
+                     NeighborCanServer=kw.get("NeighborCanServer", False), FocusOnLocalRegion=False,
+                     data_dir=os.path.join(GOLDEN, "small_city", "data"), build_engine=False)
+    random.seed(0)
+    sim.CreateAllInstantiate()
+    assert sim.NeighborServerDeepLimit == int(z["in_params"][1])
+    assert np.array_equal(sim.city.node2cluster, z["in_node2cluster"])
+    assert np.array_equal(sim.city.nb_off, z["in_nb_off"]) and np.array_equal(sim.city.nb_idx, z["in_nb_idx"])
+    assert np.array_equal(sim.city.cost_u8, z["in_cost_u8"])
+    assert np.array_equal(sim._minute, z["in_order_minute"])
+    assert np.array_equal(sim._pickup, z["in_order_pickup"]) and np.array_equal(sim._delivery, z["in_order_delivery"])
+    assert np.array_equal([o.OrderValue for o in sim.Orders], z["in_order_value"])
+    assert np.array_equal(sim._placement, z["in_veh_loc0"])
+    assert sim._T == 148
+    assert sim.RoadCost(3, 7) == int(z["in_cost_u8"][7, 3])
+    # object API surface
+    c = sim.Clusters[0]
+    for a in ("ID", "Nodes", "Neighbor", "RebalanceNumber", "IdleVehicles", "VehiclesArrivetime", "Orders",
+              "PerRebalanceIdleVehicles", "LaterRebalanceIdleVehicles", "PerMatchIdleVehicles"):
+        assert hasattr(c, a)
+    assert sum(len(c.IdleVehicles) for c in sim.Clusters) == kw["VehiclesNumber"]
+    from vehicles_dispatch_simulator_b200 import VdsError
+    with pytest.raises(VdsError):
+        sim.SimCity()                       # no engine -> loud failure, never a CPU fallback
+
+
+_GLOO_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from vehicles_dispatch_simulator_b200.parallel import ReplicaShard
+dist.init_process_group("gloo")
+sh = ReplicaShard(3)
+stats = torch.zeros((3, 10), dtype=torch.int64)
+for i, g in enumerate(sh.global_ids()):
+    stats[i, :6] = torch.arange(6) + 100 * g
+out = sh.all_gather_returns(stats)
+assert out.shape == (6, 6)
+for g in range(6):
+    assert out[g].tolist() == [100 * g + j for j in range(6)], out
+assert sh.first_replica == 3 * dist.get_rank() and sh.total == 6
+dist.destroy_process_group()
+print("ok")
+"""
+
+
+def test_replica_shard_all_gather_gloo_world2(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_GLOO_WORKER)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29731", str(script), ROOT]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("ok") == 2
+
+
+def test_philox_known_answers():
+    from oracle.synth_ref import philox4x32_10
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for c, k, exp in kat:            # Random123 kat_vectors, philox4x32 10 rounds
+        assert tuple(int(x) for x in philox4x32_10(*c, *k)) == exp
+
+
+def test_demand_tables_shape():
+    from vehicles_dispatch_simulator_b200.synthetic import DemandTables, synthetic_grid_city
+    city = synthetic_grid_city(n_nodes=400)
+    t = DemandTables(city)
+    assert t.n_slots == 144 and t.ticks == 148
+    assert abs(t.mean_total - 200000) < 1e-6
+    assert (np.diff(t.slot_cdf.astype(np.int64), axis=1) >= 0).all() and (t.slot_cdf[:, -1] == 0xFFFFFFFF).all()
+    assert (np.diff(t.zipf_cdf.astype(np.int64)) >= 0).all()
+    p = np.diff(np.concatenate([[0], t.zipf_cdf.astype(np.float64)])) / 2 ** 32
+    assert p[0] > 5 * p[99]                               # heavy head (exponent 0.83)

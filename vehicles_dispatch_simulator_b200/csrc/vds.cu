@@ -254,9 +254,8 @@ __global__ void __launch_bounds__(128)
 match_local_kernel(DevParams P, int k)
 {
     const int lane = threadIdx.x & 31;
-    const long long wg = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (wg >= (long long)P.R * P.C) return;
-    const int r = (int)(wg / P.C), c = (int)(wg % P.C);
+    const int r = blockIdx.y, c = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (c >= P.C) return;
     const int *boff = P.bucket_off + (size_t)r * (P.C + 1);
     const int b0 = boff[c], m = boff[c + 1] - b0;
     if (m == 0) return;                                    // snapshots already hold len(IdleVehicles)
@@ -290,7 +289,12 @@ match_local_kernel(DevParams P, int k)
             const int o_i = __shfl_sync(FULL, oi, j);
             const uint32_t o_pd = __shfl_sync(FULL, pd, j);
             const int o_val = __shfl_sync(FULL, val, j);
-            if (live == 0) { if (lane == 0) res[o_i] = 0x0000FFFFu; rej++; rejval += o_val; continue; }
+            if (live == 0) {                               // drained mid-chunk: reject the rest of the chunk at once
+                const bool mine = lane >= j && lane < cnt;
+                if (mine) res[oi] = 0x0000FFFFu;
+                rej += cnt - j; rejval += __reduce_add_sync(FULL, mine ? val : 0);
+                break;
+            }
             const uint8_t *row = P.cost + (size_t)(o_pd & 0xFFFF) * P.nodes;   // RoadCost(loc, pickup) = cost[pickup][loc]
             uint32_t cst = DEAD32, key = DEAD32, ex = DEAD32; int idx = lane;
             if (small) {
@@ -804,8 +808,8 @@ int vds_match(vds_handle h, int tick, void *stream)
     if (tick < 0 || tick >= h->P.T) return fail(h, VDS_ERR_INVALID, "vds_match: tick out of range");
     const DevParams &P = h->P;
     if (local_mode(h)) {
-        const long long warps = (long long)P.R * P.C;
-        match_local_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, (cudaStream_t)stream>>>(P, tick);
+        dim3 grid((P.C + 3) / 4, P.R);
+        match_local_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(P, tick);
         CKL("match_local_kernel");
     } else {
         const int smem = (int)sizeof(int) * MS_WARPS * (2 * P.C + 2);
