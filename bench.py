@@ -273,33 +273,46 @@ def main():
     e2e_value = env_steps / (float(t_el.item()) * 1e-3)
     assert torch.equal(h_ret[shard.first_replica:shard.first_replica + R], ret[shard.first_replica:shard.first_replica + R].cpu())
 
-    # ---- per-kernel device times (one instrumented episode, CUDA events on the launch stream)
-    names = ("update", "match", "supply")
-    evs = {n: [] for n in names}
-    eng.reset(loc0)
-    for k in range(T):
-        for n, fn in zip(names, (eng.update, eng.match, eng.supply_expect)):
+    # ---- per-kernel device times (CUDA events on the launch stream) and the roofline of the dominant kernel
+    V, Cn = eng.V, eng.nC
+    peak, peak_src = measured_peak_gbs()
+    if eng.fused:
+        # one launch of rollout_local_kernel == one whole episode of all R replicas
+        evs = []
+        for _ in range(max(3, args.steps)):
+            eng.reset(loc0)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(); fn(k); b.record()
-            evs[n].append((a, b))
-    torch.cuda.synchronize(dev)
-    kt = {n: float(sum(a.elapsed_time(b) for a, b in evs[n])) for n in names}      # ms per episode
+            a.record(); eng.rollout(0, T); b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize(dev)
+        kt = {"rollout": float(np.mean([a.elapsed_time(b) for a, b in evs]))}          # ms per launch
+        dom, kname, launches_per_episode = "rollout", "rollout_local_kernel<%d>" % eng.rollout_threads, 1
+    else:
+        names = ("update", "match", "supply")
+        evs = {n: [] for n in names}
+        eng.reset(loc0)
+        for k in range(T):
+            for n, fn in zip(names, (eng.update, eng.match, eng.supply_expect)):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); fn(k); b.record()
+                evs[n].append((a, b))
+        torch.cuda.synchronize(dev)
+        kt = {n: float(sum(a.elapsed_time(b) for a, b in evs[n])) for n in names}      # ms per episode
+        dom, kname, launches_per_episode = "match", "match_search_kernel", T
     st = eng.stats().cpu().numpy().astype(np.float64)
     O, A, M, P = st[:, 0].sum(), st[:, 7].sum(), st[:, 8].sum(), st[:, 6].sum()
-    V, Cn = eng.V, eng.nC
-    # algorithmic bytes: B_step = 12V + 12(A+M) + 8O + 16C + P, split per kernel
+    # algorithmic bytes: B_step = 12V + 12(A+M) + 8O + 16C + P, split per phase
     bytes_k = {"update": 12.0 * V * R * T + 12 * A + 8.0 * Cn * R * T,
                "match": 12 * M + 8 * O + P + 4.0 * Cn * R * T,
                "supply": 4.0 * Cn * R * T}
     b_total = sum(bytes_k.values())
-    peak, peak_src = measured_peak_gbs()
-    dom = max(names, key=lambda n: kt[n])
-    ach = bytes_k["match"] / (kt["match"] * 1e-3) / 1e9
-    roof = {"bound": "hbm", "kernel": "match_search_kernel" if (w["ncs"] and city.depth_limit > 0) else "match_local_kernel",
+    b_dom = b_total if eng.fused else bytes_k["match"]
+    ach = b_dom / (kt[dom] * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": kname,
             "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak,
             "traffic": None,
-            "avg_launch_us": 1e3 * kt["match"] / T,
-            "algorithmic_bytes_per_launch": bytes_k["match"] / T,
+            "avg_launch_us": 1e3 * kt[dom] / launches_per_episode,
+            "algorithmic_bytes_per_launch": b_dom / launches_per_episode,
             "kernel_ms_per_episode": kt, "dominant_kernel": dom,
             "whole_tick": {"bytes_per_env_step": b_total / (R * T),
                            "achieved": b_total / (sum(kt.values()) * 1e-3) / 1e9,

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define VDS_ABI_VERSION 1
+#define VDS_ABI_VERSION 2
 
 typedef enum vds_status {
     VDS_OK = 0,
@@ -100,6 +100,13 @@ typedef struct vds_orders {
     const uint8_t  *order_value;  /* [order_replicas][N_max] RoadCost(pickup,delivery), simulator.py:341-342 */
     const int32_t  *tick_off;     /* [order_replicas][T+1]; tick k consumes [tick_off[k], tick_off[k+1]) (:912-915) */
     const int64_t  *value_total;  /* [order_replicas] sum of order_value over ALL orders (Q8) */
+    /* Derived by vds_prepare_orders (NULL = not prepared; then vds_rollout / vds_tick fall back to the
+     * three per-phase kernels).  "Cluster.Orders.append" (simulator.py:918, 973) depends only on the
+     * stream, so the stable per-(tick, pickup-cluster) bucketing is done once per stream, not per tick. */
+    const uint32_t *sorted_pd;    /* [order_replicas][N_max] order_pd of tick k stably grouped by pickup cluster */
+    const uint16_t *sorted_idx;   /* [order_replicas][N_max] index of that order inside its tick (original order) */
+    const uint16_t *cluster_off;  /* [order_replicas][T][C+1] offsets of the cluster groups inside tick k */
+    const int64_t  *tick_value;   /* [order_replicas][T] sum of order_value over the orders tick k consumes */
 } vds_orders;
 
 /* Mutable per-replica state + per-tick outputs.  Vp = vds_padded_vehicles(V). */
@@ -122,6 +129,9 @@ typedef struct vds_state {
     int32_t  *bucket_off;         /* [R][C+1] this tick's orders grouped by pickup cluster */
     uint16_t *bucket_ord;         /* [R][max_orders_per_tick] order index inside the tick, ascending per cluster */
     int32_t  *disp_seq;           /* [R] dispatch sequence inside the current tick */
+    /* optional per-tick trace of the fused rollout (NULL = off): [R][T][4][C] =
+     * PerMatchIdleVehicles, PerDispatchIdleVehicles, SupplyExpect, len(Cluster.Orders) of every tick */
+    int32_t  *trace;
 } vds_state;
 
 typedef struct vds_handle_s *vds_handle;
@@ -141,6 +151,12 @@ int  vds_bind_state(vds_handle h, const vds_state *s);
  * (replaces the OrderValue pre-computation loop, simulator.py:341-342). */
 int  vds_compute_order_values(vds_handle h, const uint32_t *order_pd, const int32_t *n_orders,
                               uint8_t *order_value, int64_t *value_total, void *stream);
+
+/* One pass over the bound order stream(s): order_value / value_total (as
+ * vds_compute_order_values) plus the derived per-(tick, cluster) layout of
+ * the vds_orders struct -- sorted_pd, sorted_idx, cluster_off, tick_value -- which must be
+ * bound as writable device buffers.  n_orders: [order_replicas] stream lengths. */
+int  vds_prepare_orders(vds_handle h, const int32_t *n_orders, void *stream);
 
 /* Reset + InitVehiclesIntoCluster with the caller's placement
  * (simulator.py:214-258).  veh_loc0: [R][V] uint16 node per vehicle. */
@@ -166,8 +182,21 @@ int  vds_dispatch(vds_handle h, int tick, const int32_t *move_off, const int32_t
                   const int32_t *move_node, int total_moves, void *stream);
 
 /* Hook-free ticks [tick0, tick0+nticks): update, match, supply_expect per tick
- * (the body of SimCity's loop, simulator.py:1048-1091, with empty hooks). */
+ * (the body of SimCity's loop, simulator.py:1048-1091, with empty hooks).
+ * With prepared orders this is ONE launch of the replica-resident rollout
+ * kernel (a replica's vehicle state lives in shared memory for all nticks);
+ * the per-cluster outputs (per_match ... n_orders) then hold the LAST tick's
+ * values, exactly what the per-phase calls would leave behind. */
 int  vds_rollout(vds_handle h, int tick0, int nticks, void *stream);
+
+/* One fused tick == vds_rollout(h, tick, 1, stream): the call an RL loop makes
+ * between two DispatchFunction hooks. */
+int  vds_tick(vds_handle h, int tick, void *stream);
+
+/* 1 if vds_rollout runs the fused replica-resident kernel for this handle. */
+int  vds_rollout_is_fused(vds_handle h);
+/* CTA width of that kernel (0 if a replica does not fit one SM's shared memory). */
+int  vds_rollout_threads(vds_handle h);
 
 /* out[R][VDS_NUM_STATS] (device): finalises SumOrderValue (simulator.py:1095-1100). */
 int  vds_stats(vds_handle h, int64_t *out, void *stream);

@@ -38,8 +38,10 @@ def policy_moves(oracle, city, tick):
     return np.array(veh, np.int32), np.array(node, np.int32)
 
 
-def lockstep(engine, oracles, loc0, dispatch=False, check_lists_every=1, ticks=None):
-    """oracles: one per replica.  Returns the number of ticks compared."""
+def lockstep(engine, oracles, loc0, dispatch=False, check_lists_every=1, ticks=None, fused=False):
+    """oracles: one per replica.  Returns the number of ticks compared.
+    fused=True drives the engine through the one-launch-per-tick path
+    (vds_tick) instead of update / match / supply_expect."""
     city = engine.city
     R = engine.R
     engine.reset(loc0)
@@ -48,19 +50,29 @@ def lockstep(engine, oracles, loc0, dispatch=False, check_lists_every=1, ticks=N
     T = engine.T if ticks is None else ticks
     for k in range(T):
         assert not oracles[0].done()
-        engine.update(k)
+        if not fused:
+            engine.update(k)
         for o in oracles:
             o.update()
-        if check_lists_every and k % check_lists_every == 0:
+        if not fused and check_lists_every and k % check_lists_every == 0:
             for r in (0, R - 1):
                 got = engine.idle_lists(r)
                 exp = oracles[r].idle_lists()
                 for c in range(city.n_clusters):
                     assert np.array_equal(got[c], exp[c]), f"idle list order tick {k} replica {r} cluster {c}"
-        engine.match(k)
-        engine.supply_expect(k)
+        if fused:
+            engine.tick(k)
+        else:
+            engine.match(k)
+            engine.supply_expect(k)
         for o in oracles:
             o.match(); o.supply_expect(); o.snapshot_pre_dispatch()
+        if fused and check_lists_every and k % check_lists_every == 0:
+            for r in (0, R - 1):
+                got = engine.idle_lists(r)
+                exp = oracles[r].idle_lists()
+                for c in range(city.n_clusters):
+                    assert np.array_equal(got[c], exp[c]), f"idle list order after match, tick {k} replica {r} cluster {c}"
         t = {n: engine.tensors[n].cpu().numpy() for n in ("per_match", "per_dispatch", "supply", "n_orders", "idle_live")}
         for r, o in enumerate(oracles):
             assert np.array_equal(t["per_match"][r], o.per_match()), f"per_match tick {k} replica {r}"
@@ -88,6 +100,57 @@ def lockstep(engine, oracles, loc0, dispatch=False, check_lists_every=1, ticks=N
         assert np.array_equal(wait, o.order_wait()), f"wait replica {r}"
         os_ = o.stats()
         assert tuple(st[r][:9]) == tuple(os_[:9]), f"stats replica {r}: {st[r]} vs {os_}"
+    return T
+
+
+def rollout_vs_oracle(engine, oracles, loc0, windows=None):
+    """Fused replica-resident rollout (engine built with trace=True) vs the
+    oracle: per-tick per-cluster trace, idle-list order at every window
+    boundary, per-order results and counters.  windows: list of tick counts
+    (default one window = the whole episode)."""
+    city, R, T, C = engine.city, engine.R, engine.T, engine.city.n_clusters
+    assert engine.fused and engine.trace is not None
+    engine.reset(loc0)
+    for r, o in enumerate(oracles):
+        o.reset(loc0 if np.ndim(loc0) == 1 else loc0[r])
+    exp = np.zeros((R, T, 4, C), np.int32)
+    k = 0
+    for wlen in (windows or [T]):
+        engine.rollout(k, wlen)
+        for kk in range(k, k + wlen):
+            for r, o in enumerate(oracles):
+                o.update(); o.match(); o.supply_expect(); o.snapshot_pre_dispatch()
+                exp[r, kk, 0], exp[r, kk, 1] = o.per_match(), o.per_dispatch()
+                exp[r, kk, 2], exp[r, kk, 3] = o.supply(), o.n_orders()
+                o.end_tick()
+        k += wlen
+        t = {n: engine.tensors[n].cpu().numpy() for n in ("per_match", "per_dispatch", "supply", "n_orders", "idle_live")}
+        for r, o in enumerate(oracles):
+            assert np.array_equal(t["per_match"][r], exp[r, k - 1, 0]), f"per_match after window ending {k}"
+            assert np.array_equal(t["per_dispatch"][r], exp[r, k - 1, 1])
+            assert np.array_equal(t["supply"][r], exp[r, k - 1, 2])
+            assert np.array_equal(t["n_orders"][r], exp[r, k - 1, 3])
+            assert np.array_equal(t["idle_live"][r], o.later_dispatch())
+        for r in (0, R - 1):
+            got, want = engine.idle_lists(r), oracles[r].idle_lists()
+            for c in range(C):
+                assert np.array_equal(got[c], want[c]), f"idle list order after tick {k - 1} replica {r} cluster {c}"
+            V = engine.V
+            assert np.array_equal(engine.tensors["veh_loc"][r, :V].cpu().numpy().astype(np.int32), oracles[r].veh_loc())
+            dest = engine.tensors["veh_dest"][r, :V].cpu().numpy().astype(np.int32)
+            assert np.array_equal(np.where(dest == 0xFFFF, -1, dest), oracles[r].veh_dest())
+    assert k == T and oracles[0].done()
+    tr = engine.trace.cpu().numpy()
+    for r in range(R):
+        for f, name in enumerate(("per_match", "per_dispatch", "supply", "n_orders")):
+            bad = np.argwhere(tr[r, :, f] != exp[r, :, f])
+            assert len(bad) == 0, f"trace {name} replica {r}: first mismatch (tick, cluster) = {bad[0]}"
+    st = engine.stats().cpu().numpy()
+    for r, o in enumerate(oracles):
+        veh, wait, delta = engine.order_results(r)
+        assert np.array_equal(veh, o.order_vehicle()), f"matched vehicle ids replica {r}"
+        assert np.array_equal(wait, o.order_wait()), f"wait replica {r}"
+        assert tuple(st[r][:9]) == tuple(o.stats()[:9]), f"stats replica {r}: {st[r]} vs {o.stats()}"
     return T
 
 

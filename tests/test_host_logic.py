@@ -25,11 +25,12 @@ def test_c_abi_exports_every_declared_symbol():
     L = _native.lib()                      # loads libvds.so (no compute, no GPU needed)
     for name in declared:
         assert hasattr(L, name), name
-    assert L.vds_abi_version() == 1
+    assert L.vds_abi_version() == 2
     assert L.vds_padded_vehicles(2001) == 2008
     # struct layouts agree with the header's field counts
     assert ctypes.sizeof(_native.Config) == 12 * 4 + 8
-    assert ctypes.sizeof(_native.State) == 17 * 8
+    assert ctypes.sizeof(_native.State) == 18 * 8
+    assert ctypes.sizeof(_native.Orders) == 8 * 8
 
 
 def test_no_cpu_fallback_without_gpu():

@@ -40,12 +40,13 @@ class Static(C.Structure):
 
 
 class Orders(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("order_pd", "order_value", "tick_off", "value_total")]
+    _fields_ = [(n, C.c_void_p) for n in ("order_pd", "order_value", "tick_off", "value_total",
+                                          "sorted_pd", "sorted_idx", "cluster_off", "tick_value")]
 
 
 STATE_FIELDS = ("veh_loc", "veh_cluster", "veh_arrive", "veh_dest", "veh_key", "order_res",
                 "per_match", "per_dispatch", "idle_live", "supply", "n_orders", "stats",
-                "idle_ent", "idle_off", "bucket_off", "bucket_ord", "disp_seq")
+                "idle_ent", "idle_off", "bucket_off", "bucket_ord", "disp_seq", "trace")
 
 
 class State(C.Structure):
@@ -55,13 +56,13 @@ class State(C.Structure):
 # every symbol include/vds.h declares (tests check the export list against this)
 EXPORTS = ("vds_abi_version", "vds_padded_vehicles", "vds_create", "vds_destroy", "vds_last_error",
            "vds_bind_static", "vds_bind_orders", "vds_bind_state", "vds_compute_order_values",
-           "vds_reset", "vds_update", "vds_match", "vds_supply_expect", "vds_dispatch", "vds_rollout",
+           "vds_prepare_orders", "vds_reset", "vds_update", "vds_match", "vds_supply_expect", "vds_dispatch", "vds_rollout", "vds_tick", "vds_rollout_is_fused", "vds_rollout_threads",
            "vds_stats", "vds_sync", "vds_launch_count", "vds_generate_orders", "vds_generate_placement")
 
 
 def build(force=False, verbose=False):
     """nvcc cross-compiles sm_100a without a GPU; output stays in-tree."""
-    deps = [SRC_PATH, HDR_PATH]
+    deps = [SRC_PATH, HDR_PATH] + [os.path.join(_HERE, "csrc", f) for f in os.listdir(os.path.join(_HERE, "csrc"))]
     if (not force and os.path.exists(LIB_PATH)
             and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps)):
         return LIB_PATH
@@ -94,12 +95,16 @@ def lib():
         "vds_bind_orders": (C.c_int, [vp, C.POINTER(Orders)]),
         "vds_bind_state": (C.c_int, [vp, C.POINTER(State)]),
         "vds_compute_order_values": (C.c_int, [vp, vp, vp, vp, vp, vp]),
+        "vds_prepare_orders": (C.c_int, [vp, vp, vp]),
         "vds_reset": (C.c_int, [vp, vp, vp]),
         "vds_update": (C.c_int, [vp, i32, vp]),
         "vds_match": (C.c_int, [vp, i32, vp]),
         "vds_supply_expect": (C.c_int, [vp, i32, vp]),
         "vds_dispatch": (C.c_int, [vp, i32, vp, vp, vp, i32, vp]),
         "vds_rollout": (C.c_int, [vp, i32, i32, vp]),
+        "vds_tick": (C.c_int, [vp, i32, vp]),
+        "vds_rollout_is_fused": (C.c_int, [vp]),
+        "vds_rollout_threads": (C.c_int, [vp]),
         "vds_stats": (C.c_int, [vp, vp, vp]),
         "vds_sync": (C.c_int, [vp, vp]),
         "vds_launch_count": (i64, [vp]),

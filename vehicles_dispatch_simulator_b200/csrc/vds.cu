@@ -46,12 +46,15 @@ struct DevParams {
     uint16_t *veh_loc, *veh_cluster, *veh_arrive, *veh_dest; uint32_t *veh_key;
     uint32_t *order_res; int *per_match, *per_dispatch, *idle_live, *supply, *n_orders;
     long long *stats; uint2 *idle_ent; int *idle_off, *bucket_off; uint16_t *bucket_ord; int *disp_seq;
+    // derived order layout (vds_prepare_orders) + optional rollout trace
+    const uint32_t *spd; const uint16_t *sord; const uint16_t *coff; const long long *tick_value; int *trace;
 };
 
 struct vds_handle_s {
     vds_config cfg;
     DevParams P;
-    bool have_static, have_orders, have_state;
+    bool have_static, have_orders, have_state, have_sorted, prepared;
+    int roll_threads, roll_smem;
     char err[512];
     int64_t launches;
     int sm_count;
@@ -576,6 +579,8 @@ __global__ void order_value_kernel(DevParams P, const uint32_t *opd, const int *
     if ((threadIdx.x & 31) == 0 && s) atomicAddLL(vtotal + ro, s);
 }
 
+#include "rollout.cuh"
+
 // ------------------------------------------- synthetic Didi-shaped generator
 struct Philox { uint32_t c[4]; };
 __host__ __device__ inline Philox philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1)
@@ -715,6 +720,18 @@ int vds_create(const vds_config *cfg, vds_handle *out)
     const int Cp = (P.C + 3) & ~3;
     const int upd_smem = (int)sizeof(int) * (4 * Cp + 8 + 16 + UPD_WARPS * Cp);
     CK(cudaFuncSetAttribute(update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, upd_smem));
+    const int prep_smem = (int)sizeof(int) * (2 * Cp + 4 + 16 + PREP_WARPS * Cp);
+    CK(cudaFuncSetAttribute(prepare_orders_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, prep_smem));
+    // replica-resident rollout kernel: pick the CTA width from how many replicas fit one SM
+    h->roll_smem = roll_layout(P.Vp, P.C).total;
+    h->roll_threads = 0;
+    if (h->roll_smem <= (int)prop.sharedMemPerBlockOptin) {
+        const int per_sm = (int)prop.sharedMemPerMultiprocessor / (h->roll_smem + 1024);
+        h->roll_threads = per_sm >= 6 ? 128 : per_sm >= 3 ? 256 : 512;
+        CK(cudaFuncSetAttribute(rollout_local_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
+        CK(cudaFuncSetAttribute(rollout_local_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
+        CK(cudaFuncSetAttribute(rollout_local_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
+    }
     return VDS_OK;
 }
 
@@ -733,6 +750,9 @@ int vds_bind_orders(vds_handle h, const vds_orders *o)
     if (!h || !o || !o->order_pd || !o->order_value || !o->tick_off || !o->value_total)
         return fail(h, VDS_ERR_INVALID, "vds_bind_orders: null pointer");
     h->P.opd = o->order_pd; h->P.oval = o->order_value; h->P.toff = o->tick_off; h->P.vtotal = (const long long *)o->value_total;
+    h->P.spd = o->sorted_pd; h->P.sord = o->sorted_idx; h->P.coff = o->cluster_off; h->P.tick_value = (const long long *)o->tick_value;
+    h->have_sorted = o->sorted_pd && o->sorted_idx && o->cluster_off && o->tick_value;
+    h->prepared = false;
     h->have_orders = true; return VDS_OK;
 }
 int vds_bind_state(vds_handle h, const vds_state *s)
@@ -750,7 +770,7 @@ int vds_bind_state(vds_handle h, const vds_state *s)
     P.veh_key = s->veh_key; P.order_res = s->order_res; P.per_match = s->per_match; P.per_dispatch = s->per_dispatch;
     P.idle_live = s->idle_live; P.supply = s->supply; P.n_orders = s->n_orders; P.stats = (long long *)s->stats;
     P.idle_ent = (uint2 *)s->idle_ent; P.idle_off = s->idle_off; P.bucket_off = s->bucket_off;
-    P.bucket_ord = s->bucket_ord; P.disp_seq = s->disp_seq;
+    P.bucket_ord = s->bucket_ord; P.disp_seq = s->disp_seq; P.trace = s->trace;
     h->have_state = true; return VDS_OK;
 }
 
@@ -773,6 +793,27 @@ int vds_compute_order_values(vds_handle h, const uint32_t *order_pd, const int32
     dim3 grid(h->sm_count * 2, h->P.OR);
     order_value_kernel<<<grid, 256, 0, st>>>(h->P, order_pd, n_orders, order_value, (long long *)value_total);
     CKL("order_value_kernel");
+    return VDS_OK;
+}
+
+int vds_prepare_orders(vds_handle h, const int32_t *n_orders, void *stream)
+{
+    if (!h || !h->have_static || !h->have_orders || !n_orders)
+        return fail(h, VDS_ERR_INVALID, "vds_prepare_orders: bind_static / bind_orders first");
+    if (!h->have_sorted)
+        return fail(h, VDS_ERR_INVALID, "vds_prepare_orders: vds_orders.sorted_pd / sorted_idx / cluster_off / tick_value are NULL");
+    if (h->P.maxOT > 65535) return fail(h, VDS_ERR_INVALID, "vds_prepare_orders: max_orders_per_tick > 65535");
+    cudaStream_t st = (cudaStream_t)stream;
+    const DevParams &P = h->P;
+    CK(cudaMemsetAsync((void *)P.vtotal, 0, sizeof(int64_t) * P.OR, st));
+    const int Cp = (P.C + 3) & ~3;
+    const int smem = (int)sizeof(int) * (2 * Cp + 4 + 16 + PREP_WARPS * Cp);
+    dim3 grid(P.T, P.OR);
+    prepare_orders_kernel<<<grid, PREP_THREADS, smem, st>>>(P, n_orders, (uint8_t *)P.oval, (long long *)P.vtotal,
+                                                           (uint32_t *)P.spd, (uint16_t *)P.sord, (uint16_t *)P.coff,
+                                                           (long long *)P.tick_value);
+    CKL("prepare_orders_kernel");
+    h->prepared = true;
     return VDS_OK;
 }
 
@@ -839,10 +880,28 @@ int vds_dispatch(vds_handle h, int tick, const int32_t *move_off, const int32_t 
     return VDS_OK;
 }
 
+int vds_rollout_is_fused(vds_handle h)
+{
+    return h && local_mode(h) && h->prepared && h->roll_threads > 0;
+}
+
+int vds_rollout_threads(vds_handle h) { return h ? h->roll_threads : 0; }
+
 int vds_rollout(vds_handle h, int tick0, int nticks, void *stream)
 {
     int rc = ready(h, true); if (rc) return rc;
     if (tick0 < 0 || nticks < 0 || tick0 + nticks > h->P.T) return fail(h, VDS_ERR_INVALID, "vds_rollout: tick range");
+    if (nticks == 0) return VDS_OK;
+    if (vds_rollout_is_fused(h)) {
+        cudaStream_t st = (cudaStream_t)stream;
+        switch (h->roll_threads) {
+        case 128: rollout_local_kernel<128><<<h->P.R, 128, h->roll_smem, st>>>(h->P, tick0, nticks); break;
+        case 256: rollout_local_kernel<256><<<h->P.R, 256, h->roll_smem, st>>>(h->P, tick0, nticks); break;
+        default:  rollout_local_kernel<512><<<h->P.R, 512, h->roll_smem, st>>>(h->P, tick0, nticks); break;
+        }
+        CKL("rollout_local_kernel");
+        return VDS_OK;
+    }
     for (int k = tick0; k < tick0 + nticks; k++) {
         if ((rc = vds_update(h, k, stream))) return rc;
         if ((rc = vds_match(h, k, stream))) return rc;
@@ -850,6 +909,8 @@ int vds_rollout(vds_handle h, int tick0, int nticks, void *stream)
     }
     return VDS_OK;
 }
+
+int vds_tick(vds_handle h, int tick, void *stream) { return vds_rollout(h, tick, 1, stream); }
 
 int vds_stats(vds_handle h, int64_t *out, void *stream)
 {

@@ -101,7 +101,7 @@ def _ptr(t):
 class DispatchEngine:
     def __init__(self, city, n_vehicles, replicas=1, period=10, ticks=148, max_orders=1,
                  per_replica_orders=False, max_orders_per_tick=4096,
-                 reject_threshold=N.PARITY_THRESHOLD, device=0):
+                 reject_threshold=N.PARITY_THRESHOLD, device=0, trace=False):
         if not torch.cuda.is_available():
             raise N.VdsError("DispatchEngine needs a CUDA device (sm_100a); there is no CPU fallback")
         self.L = N.lib()
@@ -142,7 +142,14 @@ class DispatchEngine:
             self.tick_off = z((self.OR, self.T + 1), torch.int32)
             self.value_total = z((self.OR,), torch.int64)
             self.n_orders_total = z((self.OR,), torch.int32)
-            od = N.Orders(self.order_pd.data_ptr(), self.order_value.data_ptr(), self.tick_off.data_ptr(), self.value_total.data_ptr())
+            # derived per-(tick, cluster) layout, filled by vds_prepare_orders
+            self.sorted_pd = z((self.OR, self.Nmax), torch.uint32)
+            self.sorted_idx = z((self.OR, self.Nmax), torch.uint16)
+            self.cluster_off = z((self.OR, self.T, self.nC + 1), torch.uint16)
+            self.tick_value = z((self.OR, self.T), torch.int64)
+            od = N.Orders(self.order_pd.data_ptr(), self.order_value.data_ptr(), self.tick_off.data_ptr(),
+                          self.value_total.data_ptr(), self.sorted_pd.data_ptr(), self.sorted_idx.data_ptr(),
+                          self.cluster_off.data_ptr(), self.tick_value.data_ptr())
             self._ck(self.L.vds_bind_orders(self.h, C.byref(od)))
             # ---- state
             R, Vp, Cn = self.R, self.Vp, self.nC
@@ -156,7 +163,10 @@ class DispatchEngine:
                 idle_ent=z((R, Vp, 2), torch.uint32), idle_off=z((R, Cn + 1), torch.int32),
                 bucket_off=z((R, Cn + 1), torch.int32), bucket_ord=z((R, self.maxOT), torch.uint16),
                 disp_seq=z((R,), torch.int32))
-            s = N.State(*[self.tensors[f].data_ptr() for f in N.STATE_FIELDS])
+            # optional per-tick trace of the fused rollout: [R, T, 4, C]
+            self.trace = z((R, self.T, 4, Cn), torch.int32) if trace else None
+            s = N.State(*([self.tensors[f].data_ptr() for f in N.STATE_FIELDS[:-1]]
+                          + [self.trace.data_ptr() if trace else None]))
             self._ck(self.L.vds_bind_state(self.h, C.byref(s)))
             self._stats_out = z((R, N.VDS_NUM_STATS), torch.int64)
 
@@ -203,8 +213,9 @@ class DispatchEngine:
             self._compute_values()
 
     def _compute_values(self):
-        self._ck(self.L.vds_compute_order_values(self.h, _ptr(self.order_pd), _ptr(self.n_orders_total),
-                                                 _ptr(self.order_value), _ptr(self.value_total), self._stream()))
+        """Order values + the per-(tick, cluster) layout the fused rollout reads
+        (one pass over the stream; once per stream, not per tick)."""
+        self._ck(self.L.vds_prepare_orders(self.h, _ptr(self.n_orders_total), self._stream()))
 
     def generate_orders(self, tables, seed=1234, first_replica=0):
         """Per-replica synthetic Didi-shaped streams, generated on device
@@ -273,8 +284,22 @@ class DispatchEngine:
         self._ck(self.L.vds_dispatch(self.h, int(k), _ptr(mo), _ptr(mv), _ptr(mn), int(mv.numel()), self._stream()))
 
     def rollout(self, tick0=0, nticks=None):
+        """Hook-free ticks [tick0, tick0+nticks).  Depth-0 engines run ONE launch
+        of the replica-resident kernel (see csrc/rollout.cuh)."""
         nticks = self.T - tick0 if nticks is None else nticks
         self._ck(self.L.vds_rollout(self.h, int(tick0), int(nticks), self._stream()))
+
+    def tick(self, k):
+        """One fused tick (update + match + supply_expect)."""
+        self._ck(self.L.vds_tick(self.h, int(k), self._stream()))
+
+    @property
+    def fused(self):
+        return bool(self.L.vds_rollout_is_fused(self.h))
+
+    @property
+    def rollout_threads(self):
+        return int(self.L.vds_rollout_threads(self.h))
 
     def stats(self):
         """int64 [R, 10] device tensor (see _native.STAT_NAMES)."""
