@@ -84,8 +84,26 @@ __device__ __forceinline__ void block_scan_u32(const uint32_t *cnt, uint32_t *of
     __syncthreads();
 }
 
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS)
+// commit of one match (simulator.py:946-965) on the shared-memory vehicle record
+struct RollCommit {
+    uint16_t *arrive, *node, *clus; uint32_t *key; uint16_t *g_loc; uint32_t *res;
+    int k, pm1; uint32_t magic;
+    __device__ __forceinline__ void commit(uint32_t ex, uint32_t wait, int o_val, unsigned dnode, int o_dcl, int o_idx) const
+    {
+        const unsigned v = ex & 0xFFFF;
+        unsigned d = ((wait + (unsigned)o_val + (unsigned)pm1) * magic) >> 20;     // ceil((wait + value) / period), SURVEY Q6
+        if (d < 1) d = 1;
+        g_loc[v] = (uint16_t)(ex >> 16);                     // LocationNode unchanged until arrival (write-through)
+        arrive[v] = (uint16_t)((k + d) | 0x8000);
+        node[v] = (uint16_t)dnode;
+        clus[v] = (uint16_t)o_dcl;
+        key[v] = ((uint32_t)k << 21) | (uint32_t)o_idx;
+        res[o_idx] = v | (wait << 16) | (d << 24);
+    }
+};
+
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
 rollout_local_kernel(DevParams P, int k0, int nticks)
 {
     constexpr int NW = THREADS / 32;
@@ -131,9 +149,11 @@ rollout_local_kernel(DevParams P, int k0, int nticks)
         }
         if (tid < 8) acc[tid] = 0;
     }
-    // per-warp episode accumulators (lane-uniform)
-    unsigned long long a_wait = 0, a_look = 0, a_val = 0;
-    unsigned a_match = 0, a_arrive = 0;
+    // per-THREAD window accumulators, reduced once at window end
+    unsigned long long a_wait = 0, a_look = 0, a_val = 0, a_match = 0;
+    unsigned a_arrive = 0;
+    const bool no_timeout = P.threshold >= 255;       // cost bytes are <= 255: "cost > threshold" can never fire
+    const uint32_t thr32 = P.threshold > 0xFFFFFFF0LL ? 0xFFFFFFF0u : (P.threshold < 0 ? 0u : (uint32_t)P.threshold);
     long long a_orders = 0, a_tickval = 0;          // thread 0 only
     __syncthreads();
 
@@ -221,7 +241,12 @@ rollout_local_kernel(DevParams P, int k0, int nticks)
         __syncthreads();
 
         // ---- phase 6: match.  cluster c = (slot * NW + w), slot = round * 32 + lane
-        unsigned t_match = 0, t_val = 0;
+        unsigned t_match = 0, t_val = 0, t_wait = 0, t_look = 0;      // per-THREAD, reduced at window end
+        const uint32_t *spd_t = spd_base + tb;
+        const uint16_t *sidx_t = sidx_base + tb;
+        RollCommit cm;
+        cm.arrive = arrive; cm.node = node; cm.clus = clus; cm.key = key; cm.g_loc = P.veh_loc + vb;
+        cm.res = res_base + tb; cm.k = k; cm.magic = P.period_magic; cm.pm1 = P.period - 1;
         for (int base = 0; base * NW < C; base += 32) {
             const int c_l = (base + lane) * NW + w;
             int m_l = 0, n_l = 0, b0_l = 0, i0_l = 0;
@@ -231,22 +256,75 @@ rollout_local_kernel(DevParams P, int k0, int nticks)
                 n_l = (int)icnt[c_l]; i0_l = (int)ioff[c_l] - n_l;
             }
             const bool act_l = m_l > 0 && n_l > 0;
-            if (act_l) { pd0_l = spd_base[tb + b0_l]; idx0_l = sidx_base[tb + b0_l]; }
+            if (act_l) { pd0_l = spd_t[b0_l]; idx0_l = sidx_t[b0_l]; }
             unsigned active = __ballot_sync(FULL, act_l);
+
+            // -- lane-parallel path: a cluster with <= 4 idle vehicles is matched by ONE lane
+            //    (all cost gathers of its <= 4 x 4 (order, vehicle) pairs in flight at once)
+            const bool lp_l = act_l && n_l <= 4 && (no_timeout || m_l <= 4);
+            const unsigned lp_mask = __ballot_sync(FULL, lp_l);
+            if (lp_mask) {
+                if (lp_l) {
+                    const int nord = no_timeout ? min(m_l, n_l) : m_l;          // orders that can still find a vehicle
+                    uint32_t e[4], kk[4], pd[4], cst[4][4]; int ix[4], val[4], dcl[4];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) { e[i] = ROLL_DEAD; if (i < n_l) e[i] = ent[i0_l + i]; }
+                    pd[0] = pd0_l; ix[0] = idx0_l;
+#pragma unroll
+                    for (int j = 1; j < 4; j++) { pd[j] = 0; ix[j] = 0; if (j < nord) { pd[j] = spd_t[b0_l + j]; ix[j] = sidx_t[b0_l + j]; } }
+#pragma unroll
+                    for (int i = 0; i < 4; i++) { kk[i] = ROLL_DEAD; if (i < n_l) kk[i] = key[e[i] & 0xFFFF]; }
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        val[j] = 0; dcl[j] = 0;
+#pragma unroll
+                        for (int i = 0; i < 4; i++) cst[j][i] = ROLL_DEAD;
+                        if (j < nord) {
+                            const unsigned pn = pd[j] & 0xFFFF, dn = pd[j] >> 16;
+                            const uint8_t *row = P.cost + (size_t)pn * P.nodes;
+                            val[j] = P.cost[(size_t)dn * P.nodes + pn];
+                            dcl[j] = P.n2c[dn];
+#pragma unroll
+                            for (int i = 0; i < 4; i++) if (i < n_l) cst[j][i] = row[e[i] >> 16];
+                        }
+                    }
+                    unsigned alive = (1u << n_l) - 1u;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        if (j < nord && alive) {
+                            t_look += __popc(alive);
+                            uint32_t best = ROLL_DEAD, bk = ROLL_DEAD, be = 0; unsigned bbit = 0;
+#pragma unroll
+                            for (int i = 0; i < 4; i++) if (alive >> i & 1) {
+                                const uint32_t c2 = cst[j][i];
+                                if (c2 < best || (c2 == best && kk[i] < bk)) { best = c2; bk = kk[i]; be = e[i]; bbit = 1u << i; }
+                            }
+                            if (best <= thr32) {                                    // else TempMin[1] > PICKUPTIMEWINDOW: "Reject"
+                                cm.commit(be, best, val[j], pd[j] >> 16, dcl[j], ix[j]);
+                                alive &= ~bbit; t_match++; t_wait += best; t_val += val[j];
+                            }
+                        }
+                    }
+                    icnt[c_l] = __popc(alive);
+                }
+                active &= ~lp_mask;
+                __syncwarp();
+            }
+
+            // -- warp-cooperative path: lanes over the cluster's idle slots
             while (active) {
                 const int t = __ffs(active) - 1; active &= active - 1;
-                const int c = (base + t) * NW + w;
                 const int m = __shfl_sync(FULL, m_l, t), n = __shfl_sync(FULL, n_l, t);
                 const int b0 = __shfl_sync(FULL, b0_l, t), i0 = __shfl_sync(FULL, i0_l, t);
                 const uint32_t pd0 = __shfl_sync(FULL, pd0_l, t);
                 const int idx0 = __shfl_sync(FULL, idx0_l, t);
                 // orders 1.. of this cluster (only needed while vehicles remain): issue now, use later
                 uint32_t pdv = 0; int idxv = 0;
-                const bool more = m > 1 && (n > 1 || P.threshold < 256);   // a timeout reject does not consume a vehicle
+                const bool more = m > 1 && (n > 1 || !no_timeout);     // a timeout reject does not consume a vehicle
                 const bool small = n <= 32;
-                uint32_t e = ROLL_DEAD;
-                if (small && lane < n) e = ent[i0 + lane];
-                if (more && lane < m && lane > 0) { pdv = spd_base[tb + b0 + lane]; idxv = sidx_base[tb + b0 + lane]; }
+                uint32_t e = ROLL_DEAD, ekey = ROLL_DEAD;
+                if (small && lane < n) { e = ent[i0 + lane]; ekey = key[e & 0xFFFF]; }
+                if (more && lane < m && lane > 0) { pdv = spd_t[b0 + lane]; idxv = sidx_t[b0 + lane]; }
                 int live = n;
                 for (int j = 0; j < m && live > 0; j++) {
                     uint32_t o_pd; int o_idx;
@@ -254,19 +332,20 @@ rollout_local_kernel(DevParams P, int k0, int nticks)
                     else {
                         if ((j & 31) == 0) {                             // next chunk of the cluster's orders
                             pdv = 0; idxv = 0;
-                            if (j + lane < m) { pdv = spd_base[tb + b0 + j + lane]; idxv = sidx_base[tb + b0 + j + lane]; }
+                            if (j + lane < m) { pdv = spd_t[b0 + j + lane]; idxv = sidx_t[b0 + j + lane]; }
                         }
                         o_pd = __shfl_sync(FULL, pdv, j & 31); o_idx = __shfl_sync(FULL, idxv, j & 31);
                     }
-                    const int pnode = o_pd & 0xFFFF, dnode = o_pd >> 16;
+                    const unsigned pnode = o_pd & 0xFFFF, dnode = o_pd >> 16;
                     const uint8_t *row = P.cost + (size_t)pnode * P.nodes;       // RoadCost(loc, pickup) = cost[pickup][loc]
                     const int o_val = P.cost[(size_t)dnode * P.nodes + pnode];   // RoadCost(pickup, delivery) (:341-342)
                     const int o_dcl = P.n2c[dnode];
-                    uint32_t cst = ROLL_DEAD, ex = ROLL_DEAD; int idx = 0;
-                    uint32_t bkey = ROLL_DEAD;
+                    uint32_t cst = ROLL_DEAD, ex = e; int idx = 0;
+                    uint32_t bkey = ekey;
                     if (small) {
-                        if (e != ROLL_DEAD) { cst = row[e >> 16]; ex = e; }
+                        if (e != ROLL_DEAD) cst = row[e >> 16];
                     } else {
+                        bkey = ROLL_DEAD;
                         for (int q = lane; q < n; q += 32) {
                             const uint32_t t2 = ent[i0 + q];
                             if (t2 != ROLL_DEAD) {
@@ -278,34 +357,26 @@ rollout_local_kernel(DevParams P, int k0, int nticks)
                             }
                         }
                     }
-                    a_look += (unsigned)live;
+                    if (lane == 0) t_look += (unsigned)live;
                     const uint32_t mn = __reduce_min_sync(FULL, cst);
-                    if ((long long)mn > P.threshold) continue;               // TempMin[1] > PICKUPTIMEWINDOW (:943): stays "Reject"
+                    if (mn > thr32) continue;                                // TempMin[1] > PICKUPTIMEWINDOW (:943): stays "Reject"
                     unsigned tied = __ballot_sync(FULL, cst == mn);
                     if (tied & (tied - 1)) {                                 // cost tie: first in IdleVehicles order wins (Q5)
-                        if (small) bkey = (cst == mn) ? key[ex & 0xFFFF] : ROLL_DEAD;
                         const uint32_t kmin = __reduce_min_sync(FULL, cst == mn ? bkey : ROLL_DEAD);
                         tied = __ballot_sync(FULL, cst == mn && bkey == kmin);
                     }
-                    const int win = __ffs(tied) - 1;
-                    if (lane == win) {
-                        const int v = ex & 0xFFFF;
-                        int d = ((int)mn + o_val + P.period - 1) / P.period; if (d < 1) d = 1;
-                        P.veh_loc[vb + v] = (uint16_t)(ex >> 16);            // LocationNode unchanged until arrival
-                        arrive[v] = (uint16_t)((k + d) | 0x8000);
-                        node[v] = (uint16_t)dnode;
-                        clus[v] = (uint16_t)o_dcl;
-                        key[v] = ((uint32_t)k << 21) | (uint32_t)o_idx;
-                        res_base[tb + o_idx] = (uint32_t)v | (mn << 16) | ((uint32_t)d << 24);
+                    if (lane == __ffs(tied) - 1) {
+                        cm.commit(ex, mn, o_val, dnode, o_dcl, o_idx);
                         if (small) e = ROLL_DEAD; else ent[i0 + idx] = ROLL_DEAD;   // IdleVehicles.remove (:963)
+                        t_match++; t_wait += mn; t_val += o_val;
                     }
                     if (!small) __syncwarp();
-                    live--; t_match++; a_wait += mn; t_val += o_val;
+                    live--;
                 }
-                if (lane == 0) icnt[c] = (uint32_t)live;                     // len(IdleVehicles) after the match phase
+                if (lane == 0) icnt[(base + t) * NW + w] = (uint32_t)live;   // len(IdleVehicles) after the match phase
             }
         }
-        a_match += t_match; a_val += t_val;
+        a_match += t_match; a_val += t_val; a_wait += t_wait; a_look += t_look;
         if (tid == 0) { a_orders += n_tick; a_tickval += P.tick_value[(size_t)ro * P.T + k]; }
         __syncthreads();
 
@@ -364,8 +435,12 @@ rollout_local_kernel(DevParams P, int k0, int nticks)
             g_key[2 * g] = reinterpret_cast<uint4 *>(key)[2 * g];
             g_key[2 * g + 1] = reinterpret_cast<uint4 *>(key)[2 * g + 1];
         }
+        for (int d = 16; d; d >>= 1) {
+            a_match += __shfl_xor_sync(FULL, a_match, d); a_wait += __shfl_xor_sync(FULL, a_wait, d);
+            a_val += __shfl_xor_sync(FULL, a_val, d); a_look += __shfl_xor_sync(FULL, a_look, d);
+        }
         if (lane == 0) {
-            atomicAdd(&acc[0], (unsigned long long)a_match); atomicAdd(&acc[1], a_wait);
+            atomicAdd(&acc[0], a_match); atomicAdd(&acc[1], a_wait);
             atomicAdd(&acc[2], a_val); atomicAdd(&acc[3], a_look);
         }
         const unsigned arr_w = __reduce_add_sync(FULL, a_arrive);

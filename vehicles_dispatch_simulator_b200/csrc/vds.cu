@@ -39,7 +39,7 @@
 #define UPD_WARPS (UPD_THREADS / 32)
 
 struct DevParams {
-    int R, V, Vp, C, nodes, Nmax, T, period, depth, ncs, OR, maxOT;
+    int R, V, Vp, C, nodes, Nmax, T, period, depth, ncs, OR, maxOT; unsigned period_magic;
     long long threshold;
     const uint8_t *cost; const uint16_t *n2c; const int *soff; const uint16_t *sidx;
     const uint32_t *opd; const uint8_t *oval; const int *toff; const long long *vtotal;
@@ -717,6 +717,11 @@ int vds_create(const vds_config *cfg, vds_handle *out)
     P.nodes = cfg->nodes; P.Nmax = cfg->max_orders; P.T = cfg->ticks; P.period = cfg->period_min;
     P.depth = cfg->depth_limit; P.ncs = cfg->neighbor_can_server ? 1 : 0; P.OR = cfg->order_replicas;
     P.maxOT = cfg->max_orders_per_tick; P.threshold = cfg->reject_threshold;
+    // floor(x / period) == (x * magic) >> 20 for every x the commit can produce (x <= 255 + 255 + period - 1)
+    P.period_magic = (1u << 20) / (unsigned)P.period + 1u;
+    for (unsigned x = 0; x < 512u + (unsigned)P.period; x++)
+        if (((x * P.period_magic) >> 20) != x / (unsigned)P.period)
+            return fail(h, VDS_ERR_INVALID, "vds_create: period_min outside the exact-reciprocal range");
     const int Cp = (P.C + 3) & ~3;
     const int upd_smem = (int)sizeof(int) * (4 * Cp + 8 + 16 + UPD_WARPS * Cp);
     CK(cudaFuncSetAttribute(update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, upd_smem));
@@ -728,9 +733,9 @@ int vds_create(const vds_config *cfg, vds_handle *out)
     if (h->roll_smem <= (int)prop.sharedMemPerBlockOptin) {
         const int per_sm = (int)prop.sharedMemPerMultiprocessor / (h->roll_smem + 1024);
         h->roll_threads = per_sm >= 6 ? 128 : per_sm >= 3 ? 256 : 512;
-        CK(cudaFuncSetAttribute(rollout_local_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
-        CK(cudaFuncSetAttribute(rollout_local_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
-        CK(cudaFuncSetAttribute(rollout_local_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
+        CK(cudaFuncSetAttribute(rollout_local_kernel<128, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
+        CK(cudaFuncSetAttribute(rollout_local_kernel<256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
+        CK(cudaFuncSetAttribute(rollout_local_kernel<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
     }
     return VDS_OK;
 }
@@ -895,9 +900,9 @@ int vds_rollout(vds_handle h, int tick0, int nticks, void *stream)
     if (vds_rollout_is_fused(h)) {
         cudaStream_t st = (cudaStream_t)stream;
         switch (h->roll_threads) {
-        case 128: rollout_local_kernel<128><<<h->P.R, 128, h->roll_smem, st>>>(h->P, tick0, nticks); break;
-        case 256: rollout_local_kernel<256><<<h->P.R, 256, h->roll_smem, st>>>(h->P, tick0, nticks); break;
-        default:  rollout_local_kernel<512><<<h->P.R, 512, h->roll_smem, st>>>(h->P, tick0, nticks); break;
+        case 128: rollout_local_kernel<128, 7><<<h->P.R, 128, h->roll_smem, st>>>(h->P, tick0, nticks); break;
+        case 256: rollout_local_kernel<256, 3><<<h->P.R, 256, h->roll_smem, st>>>(h->P, tick0, nticks); break;
+        default:  rollout_local_kernel<512, 1><<<h->P.R, 512, h->roll_smem, st>>>(h->P, tick0, nticks); break;
         }
         CKL("rollout_local_kernel");
         return VDS_OK;
