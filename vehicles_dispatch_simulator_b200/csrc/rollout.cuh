@@ -152,6 +152,9 @@ rollout_local_kernel(DevParams P, int k0, int nticks)
     // per-THREAD window accumulators, reduced once at window end
     unsigned long long a_wait = 0, a_look = 0, a_val = 0, a_match = 0;
     unsigned a_arrive = 0;
+    const uint8_t *__restrict__ cost = P.cost;
+    const uint16_t *__restrict__ n2c = P.n2c;
+    const uint32_t nodes_u = (uint32_t)P.nodes;       // nodes <= 65535: pickup * nodes + loc fits 32 bits
     const bool no_timeout = P.threshold >= 255;       // cost bytes are <= 255: "cost > threshold" can never fire
     const uint32_t thr32 = P.threshold > 0xFFFFFFF0LL ? 0xFFFFFFF0u : (P.threshold < 0 ? 0u : (uint32_t)P.threshold);
     long long a_orders = 0, a_tickval = 0;          // thread 0 only
@@ -167,11 +170,14 @@ rollout_local_kernel(DevParams P, int k0, int nticks)
 #pragma unroll
         for (int i = 0; i < OPT; i++) { const int c = tid + i * THREADS; my_off[i] = c <= C ? coff[c] : 0; }
 
-        // ---- phase 1: clear per-cluster counters
-        for (int i = tid; i < Cp; i += THREADS) icnt[i] = 0;
-        __syncthreads();
-
-        // ---- phase 2: UpdateFunction: arrivals become idle; count idle vehicles per cluster
+        // ---- phase 1+2: UpdateFunction: arrivals become idle.  icnt[c] = len(IdleVehicles): counted from
+        //      scratch on the first tick of the window, afterwards carried over from the previous match phase
+        //      (live count) and only incremented by this tick's arrivals.
+        const bool first = (k == k0);
+        if (first) {
+            for (int i = tid; i < Cp; i += THREADS) icnt[i] = 0;
+            __syncthreads();
+        }
         for (int g = tid; g < ngroups; g += THREADS) {
             U16x8 a; a.v = reinterpret_cast<uint4 *>(arrive)[g];
             unsigned arriving = 0, idle = 0;
@@ -191,11 +197,12 @@ rollout_local_kernel(DevParams P, int k0, int nticks)
                     key[v] = ((uint32_t)at << 21) | ((uint32_t)(63 - dt) << 15) | (kk & 0x7FFF);
                     a.h[j] = IDLE16;                                      // objects.py:84-89 (node already holds DeliveryPoint)
                     a_arrive++;
+                    if (!first) atomicAdd(&icnt[clus[v]], 1u);
                 }
                 reinterpret_cast<uint4 *>(arrive)[g] = a.v;
                 idle |= arriving;
             }
-            if (idle) {
+            if (first && idle) {
                 U16x8 c; c.v = reinterpret_cast<uint4 *>(clus)[g];
 #pragma unroll
                 for (int j = 0; j < 8; j++) if (idle >> j & 1) atomicAdd(&icnt[c.h[j]], 1u);
@@ -281,11 +288,11 @@ rollout_local_kernel(DevParams P, int k0, int nticks)
                         for (int i = 0; i < 4; i++) cst[j][i] = ROLL_DEAD;
                         if (j < nord) {
                             const unsigned pn = pd[j] & 0xFFFF, dn = pd[j] >> 16;
-                            const uint8_t *row = P.cost + (size_t)pn * P.nodes;
-                            val[j] = P.cost[(size_t)dn * P.nodes + pn];
-                            dcl[j] = P.n2c[dn];
+                            const uint32_t rowoff = pn * nodes_u;
+                            val[j] = cost[dn * nodes_u + pn];
+                            dcl[j] = n2c[dn];
 #pragma unroll
-                            for (int i = 0; i < 4; i++) if (i < n_l) cst[j][i] = row[e[i] >> 16];
+                            for (int i = 0; i < 4; i++) if (i < n_l) cst[j][i] = cost[rowoff + (e[i] >> 16)];
                         }
                     }
                     unsigned alive = (1u << n_l) - 1u;
@@ -337,23 +344,25 @@ rollout_local_kernel(DevParams P, int k0, int nticks)
                         o_pd = __shfl_sync(FULL, pdv, j & 31); o_idx = __shfl_sync(FULL, idxv, j & 31);
                     }
                     const unsigned pnode = o_pd & 0xFFFF, dnode = o_pd >> 16;
-                    const uint8_t *row = P.cost + (size_t)pnode * P.nodes;       // RoadCost(loc, pickup) = cost[pickup][loc]
-                    const int o_val = P.cost[(size_t)dnode * P.nodes + pnode];   // RoadCost(pickup, delivery) (:341-342)
-                    const int o_dcl = P.n2c[dnode];
+                    const uint32_t rowoff = pnode * nodes_u;                     // RoadCost(loc, pickup) = cost[pickup][loc]
+                    const int o_val = cost[dnode * nodes_u + pnode];             // RoadCost(pickup, delivery) (:341-342)
+                    const int o_dcl = n2c[dnode];
                     uint32_t cst = ROLL_DEAD, ex = e; int idx = 0;
                     uint32_t bkey = ekey;
                     if (small) {
-                        if (e != ROLL_DEAD) cst = row[e >> 16];
+                        if (e != ROLL_DEAD) cst = cost[rowoff + (e >> 16)];
                     } else {
                         bkey = ROLL_DEAD;
-                        for (int q = lane; q < n; q += 32) {
-                            const uint32_t t2 = ent[i0 + q];
-                            if (t2 != ROLL_DEAD) {
-                                const uint32_t c2 = row[t2 >> 16];
-                                if (c2 <= cst) {
-                                    const uint32_t k2 = key[t2 & 0xFFFF];
-                                    if (c2 < cst || k2 < bkey) { cst = c2; bkey = k2; ex = t2; idx = q; }
-                                }
+                        for (int q0 = lane; q0 < n; q0 += 128) {             // 4 independent (slot, cost) gathers in flight
+                            uint32_t t4[4], c4[4];
+#pragma unroll
+                            for (int u = 0; u < 4; u++) { t4[u] = ROLL_DEAD; if (q0 + 32 * u < n) t4[u] = ent[i0 + q0 + 32 * u]; }
+#pragma unroll
+                            for (int u = 0; u < 4; u++) { c4[u] = ROLL_DEAD; if (t4[u] != ROLL_DEAD) c4[u] = cost[rowoff + (t4[u] >> 16)]; }
+#pragma unroll
+                            for (int u = 0; u < 4; u++) if (c4[u] <= cst && t4[u] != ROLL_DEAD) {
+                                const uint32_t k2 = key[t4[u] & 0xFFFF];
+                                if (c4[u] < cst || k2 < bkey) { cst = c4[u]; bkey = k2; ex = t4[u]; idx = q0 + 32 * u; }
                             }
                         }
                     }
@@ -389,8 +398,7 @@ rollout_local_kernel(DevParams P, int k0, int nticks)
                 g_pd[i] = lv; g_lv[i] = lv;
                 if (tr) tr[C + i] = lv;
             }
-            __syncthreads();
-            for (int i = tid; i < Cp; i += THREADS) icnt[i] = 0;
+            for (int i = tid; i < Cp; i += THREADS) ioff[i] = 0;         // ioff is free after the match phase
             __syncthreads();
             for (int g = tid; g < ngroups; g += THREADS) {
                 U16x8 a; a.v = reinterpret_cast<uint4 *>(arrive)[g];
@@ -403,12 +411,12 @@ rollout_local_kernel(DevParams P, int k0, int nticks)
                 if (hit) {
                     U16x8 c; c.v = reinterpret_cast<uint4 *>(clus)[g];
 #pragma unroll
-                    for (int j = 0; j < 8; j++) if (hit >> j & 1) atomicAdd(&icnt[c.h[j]], 1u);
+                    for (int j = 0; j < 8; j++) if (hit >> j & 1) atomicAdd(&ioff[c.h[j]], 1u);
                 }
             }
             __syncthreads();
             int *g_s = P.supply + (size_t)r * C;
-            for (int i = tid; i < C; i += THREADS) { g_s[i] = (int)icnt[i]; if (tr) tr[2 * C + i] = (int)icnt[i]; }
+            for (int i = tid; i < C; i += THREADS) { g_s[i] = (int)ioff[i]; if (tr) tr[2 * C + i] = (int)ioff[i]; }
             __syncthreads();
         }
     }
