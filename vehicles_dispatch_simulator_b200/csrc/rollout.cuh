@@ -33,7 +33,7 @@
 #define ROLL_DEAD 0xFFFFFFFFu
 
 struct RollLayout {
-    int key, ent, arrive, node, clus, icnt, ioff, wtot, ooff, acc, total;
+    int key, ent, arrive, node, clus, icnt, ioff, wtot, ooff, acc, wl, wl_ix, wl_pd, wl_cnt, total;
 };
 __host__ __device__ inline RollLayout roll_layout(int Vp, int C)
 {
@@ -51,6 +51,10 @@ __host__ __device__ inline RollLayout roll_layout(int Vp, int C)
     L.wtot = o;   o += 4 * 40;
     L.acc = o;    o += 8 * 8;
     L.ooff = o;   o += 2 * (Cp + 8);
+    L.wl_pd = o;  o += 4 * Cp;
+    L.wl_cnt = o; o += 16;
+    L.wl = o;     o += 2 * Cp;
+    L.wl_ix = o;  o += 2 * Cp;
     L.total = (o + 15) & ~15;
     return L;
 }
@@ -102,6 +106,61 @@ struct RollCommit {
     }
 };
 
+// A cluster with <= 4 idle vehicles is matched by ONE thread: all cost gathers of its <= 4 x 4
+// (order, vehicle) pairs are in flight at once, the greedy assignment runs in registers.
+// Kept out of line so its register footprint does not tax the warp-cooperative path.
+struct RollLane {
+    const uint32_t *ent, *key, *spd_t; const uint16_t *sidx_t, *n2c; const uint8_t *cost;
+    uint32_t nodes_u, thr32; int no_timeout;
+};
+__device__ __noinline__ uint4 roll_lane_match(RollLane q, RollCommit cm, int m_l, int n_l, int b0_l, int i0_l,
+                                              uint32_t pd0_l, int idx0_l, uint32_t *live_out)
+{
+    uint4 st = make_uint4(0, 0, 0, 0);                                // matches, wait, value, lookups
+    const int nord = q.no_timeout ? min(m_l, n_l) : m_l;              // orders that can still find a vehicle
+    uint32_t e[4], kk[4], pd[4], cst[4][4]; int ix[4], val[4], dcl[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) { e[i] = ROLL_DEAD; if (i < n_l) e[i] = q.ent[i0_l + i]; }
+    pd[0] = pd0_l; ix[0] = idx0_l;
+#pragma unroll
+    for (int j = 1; j < 4; j++) { pd[j] = 0; ix[j] = 0; if (j < nord) { pd[j] = q.spd_t[b0_l + j]; ix[j] = q.sidx_t[b0_l + j]; } }
+#pragma unroll
+    for (int i = 0; i < 4; i++) { kk[i] = ROLL_DEAD; if (i < n_l) kk[i] = q.key[e[i] & 0xFFFF]; }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        val[j] = 0; dcl[j] = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) cst[j][i] = ROLL_DEAD;
+        if (j < nord) {
+            const unsigned pn = pd[j] & 0xFFFF, dn = pd[j] >> 16;
+            const uint32_t rowoff = pn * q.nodes_u;
+            val[j] = q.cost[dn * q.nodes_u + pn];
+            dcl[j] = q.n2c[dn];
+#pragma unroll
+            for (int i = 0; i < 4; i++) if (i < n_l) cst[j][i] = q.cost[rowoff + (e[i] >> 16)];
+        }
+    }
+    unsigned alive = (1u << n_l) - 1u;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        if (j < nord && alive) {
+            st.w += __popc(alive);
+            uint32_t best = ROLL_DEAD, bk = ROLL_DEAD, be = 0; unsigned bbit = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) if (alive >> i & 1) {
+                const uint32_t c2 = cst[j][i];
+                if (c2 < best || (c2 == best && kk[i] < bk)) { best = c2; bk = kk[i]; be = e[i]; bbit = 1u << i; }
+            }
+            if (best <= q.thr32) {                                    // else TempMin[1] > PICKUPTIMEWINDOW: "Reject"
+                cm.commit(be, best, val[j], pd[j] >> 16, dcl[j], ix[j]);
+                alive &= ~bbit; st.x++; st.y += best; st.z += val[j];
+            }
+        }
+    }
+    *live_out = __popc(alive);
+    return st;
+}
+
 template <int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
 rollout_local_kernel(DevParams P, int k0, int nticks)
@@ -120,6 +179,10 @@ rollout_local_kernel(DevParams P, int k0, int nticks)
     uint32_t *wtot = reinterpret_cast<uint32_t *>(smraw + L.wtot);
     unsigned long long *acc = reinterpret_cast<unsigned long long *>(smraw + L.acc);
     uint16_t *ooff = reinterpret_cast<uint16_t *>(smraw + L.ooff);
+    uint32_t *wl_pd = reinterpret_cast<uint32_t *>(smraw + L.wl_pd);
+    uint32_t *wl_cnt = reinterpret_cast<uint32_t *>(smraw + L.wl_cnt);
+    uint16_t *wl = reinterpret_cast<uint16_t *>(smraw + L.wl);
+    uint16_t *wl_ix = reinterpret_cast<uint16_t *>(smraw + L.wl_ix);
 
     const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const size_t vb = (size_t)r * Vp;
@@ -244,6 +307,7 @@ rollout_local_kernel(DevParams P, int k0, int nticks)
         {
             uint32_t *p = res_base + tb;
             for (int i = tid; i < n_tick; i += THREADS) p[i] = 0x0000FFFFu;
+            if (tid < 4) wl_cnt[tid] = 0;
         }
         __syncthreads();
 
@@ -254,77 +318,46 @@ rollout_local_kernel(DevParams P, int k0, int nticks)
         RollCommit cm;
         cm.arrive = arrive; cm.node = node; cm.clus = clus; cm.key = key; cm.g_loc = P.veh_loc + vb;
         cm.res = res_base + tb; cm.k = k; cm.magic = P.period_magic; cm.pm1 = P.period - 1;
-        for (int base = 0; base * NW < C; base += 32) {
-            const int c_l = (base + lane) * NW + w;
-            int m_l = 0, n_l = 0, b0_l = 0, i0_l = 0;
-            uint32_t pd0_l = 0; int idx0_l = 0;
-            if (c_l < C) {
-                b0_l = ooff[c_l]; m_l = (int)ooff[c_l + 1] - b0_l;
-                n_l = (int)icnt[c_l]; i0_l = (int)ioff[c_l] - n_l;
+        RollLane lq;
+        lq.ent = ent; lq.key = key; lq.spd_t = spd_t; lq.sidx_t = sidx_t; lq.n2c = n2c; lq.cost = cost;
+        lq.nodes_u = nodes_u; lq.thr32 = thr32; lq.no_timeout = no_timeout ? 1 : 0;
+        // -- 6a: every thread classifies clusters (orders this tick? idle vehicles?) and files the active ones,
+        //    first order already fetched: clusters with <= 4 idle vehicles at the back of the work list
+        //    (one THREAD each), the others at the front (one WARP each).
+        for (int c_l = tid; c_l < C; c_l += THREADS) {
+            const int b0_l = ooff[c_l], m_l = (int)ooff[c_l + 1] - b0_l;
+            const int n_l = (int)icnt[c_l];
+            if (m_l > 0 && n_l > 0) {
+                const uint32_t pd0_l = spd_t[b0_l]; const int idx0_l = sidx_t[b0_l];
+                const bool lp = n_l <= 4 && (no_timeout || m_l <= 4);
+                const int slot = lp ? C - 1 - (int)atomicAdd(&wl_cnt[1], 1u) : (int)atomicAdd(&wl_cnt[0], 1u);
+                wl[slot] = (uint16_t)c_l; wl_pd[slot] = pd0_l; wl_ix[slot] = (uint16_t)idx0_l;
             }
-            const bool act_l = m_l > 0 && n_l > 0;
-            if (act_l) { pd0_l = spd_t[b0_l]; idx0_l = sidx_t[b0_l]; }
-            unsigned active = __ballot_sync(FULL, act_l);
-
-            // -- lane-parallel path: a cluster with <= 4 idle vehicles is matched by ONE lane
-            //    (all cost gathers of its <= 4 x 4 (order, vehicle) pairs in flight at once)
-            const bool lp_l = act_l && n_l <= 4 && (no_timeout || m_l <= 4);
-            const unsigned lp_mask = __ballot_sync(FULL, lp_l);
-            if (lp_mask) {
-                if (lp_l) {
-                    const int nord = no_timeout ? min(m_l, n_l) : m_l;          // orders that can still find a vehicle
-                    uint32_t e[4], kk[4], pd[4], cst[4][4]; int ix[4], val[4], dcl[4];
-#pragma unroll
-                    for (int i = 0; i < 4; i++) { e[i] = ROLL_DEAD; if (i < n_l) e[i] = ent[i0_l + i]; }
-                    pd[0] = pd0_l; ix[0] = idx0_l;
-#pragma unroll
-                    for (int j = 1; j < 4; j++) { pd[j] = 0; ix[j] = 0; if (j < nord) { pd[j] = spd_t[b0_l + j]; ix[j] = sidx_t[b0_l + j]; } }
-#pragma unroll
-                    for (int i = 0; i < 4; i++) { kk[i] = ROLL_DEAD; if (i < n_l) kk[i] = key[e[i] & 0xFFFF]; }
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        val[j] = 0; dcl[j] = 0;
-#pragma unroll
-                        for (int i = 0; i < 4; i++) cst[j][i] = ROLL_DEAD;
-                        if (j < nord) {
-                            const unsigned pn = pd[j] & 0xFFFF, dn = pd[j] >> 16;
-                            const uint32_t rowoff = pn * nodes_u;
-                            val[j] = cost[dn * nodes_u + pn];
-                            dcl[j] = n2c[dn];
-#pragma unroll
-                            for (int i = 0; i < 4; i++) if (i < n_l) cst[j][i] = cost[rowoff + (e[i] >> 16)];
-                        }
-                    }
-                    unsigned alive = (1u << n_l) - 1u;
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        if (j < nord && alive) {
-                            t_look += __popc(alive);
-                            uint32_t best = ROLL_DEAD, bk = ROLL_DEAD, be = 0; unsigned bbit = 0;
-#pragma unroll
-                            for (int i = 0; i < 4; i++) if (alive >> i & 1) {
-                                const uint32_t c2 = cst[j][i];
-                                if (c2 < best || (c2 == best && kk[i] < bk)) { best = c2; bk = kk[i]; be = e[i]; bbit = 1u << i; }
-                            }
-                            if (best <= thr32) {                                    // else TempMin[1] > PICKUPTIMEWINDOW: "Reject"
-                                cm.commit(be, best, val[j], pd[j] >> 16, dcl[j], ix[j]);
-                                alive &= ~bbit; t_match++; t_wait += best; t_val += val[j];
-                            }
-                        }
-                    }
-                    icnt[c_l] = __popc(alive);
-                }
-                active &= ~lp_mask;
-                __syncwarp();
+        }
+        __syncthreads();
+        {
+            const int n_lp = (int)wl_cnt[1];
+            for (int i = tid; i < n_lp; i += THREADS) {                  // dense: no idle lanes between small clusters
+                const int slot = C - 1 - i;
+                const int c_l = wl[slot];
+                const int b0_l = ooff[c_l], m_l = (int)ooff[c_l + 1] - b0_l;
+                const int n_l = (int)icnt[c_l], i0_l = (int)ioff[c_l] - n_l;
+                const uint4 st = roll_lane_match(lq, cm, m_l, n_l, b0_l, i0_l, wl_pd[slot], (int)wl_ix[slot], &icnt[c_l]);
+                t_match += st.x; t_wait += st.y; t_val += st.z; t_look += st.w;
             }
-
-            // -- warp-cooperative path: lanes over the cluster's idle slots
-            while (active) {
-                const int t = __ffs(active) - 1; active &= active - 1;
-                const int m = __shfl_sync(FULL, m_l, t), n = __shfl_sync(FULL, n_l, t);
-                const int b0 = __shfl_sync(FULL, b0_l, t), i0 = __shfl_sync(FULL, i0_l, t);
-                const uint32_t pd0 = __shfl_sync(FULL, pd0_l, t);
-                const int idx0 = __shfl_sync(FULL, idx0_l, t);
+        }
+        // -- 6b: warps pop clusters off the work list: lanes over the cluster's idle slots
+        {
+            const int n_work = (int)wl_cnt[0];
+            while (true) {
+                int slot = 0;
+                if (lane == 0) slot = (int)atomicAdd(&wl_cnt[2], 1u);
+                slot = __shfl_sync(FULL, slot, 0);
+                if (slot >= n_work) break;
+                const int c = wl[slot];
+                const uint32_t pd0 = wl_pd[slot]; const int idx0 = wl_ix[slot];
+                const int b0 = ooff[c], m = (int)ooff[c + 1] - b0;
+                const int n = (int)icnt[c], i0 = (int)ioff[c] - n;
                 // orders 1.. of this cluster (only needed while vehicles remain): issue now, use later
                 uint32_t pdv = 0; int idxv = 0;
                 const bool more = m > 1 && (n > 1 || !no_timeout);     // a timeout reject does not consume a vehicle
@@ -352,19 +385,24 @@ rollout_local_kernel(DevParams P, int k0, int nticks)
                     if (small) {
                         if (e != ROLL_DEAD) cst = cost[rowoff + (e >> 16)];
                     } else {
-                        bkey = ROLL_DEAD;
-                        for (int q0 = lane; q0 < n; q0 += 128) {             // 4 independent (slot, cost) gathers in flight
-                            uint32_t t4[4], c4[4];
+                        // branch-free: every live slot contributes (cost << 32 | idle key); 4 gathers in flight
+                        unsigned long long best = ~0ull;
+                        for (int q0 = lane; q0 < n; q0 += 128) {
+                            uint32_t t4[4], c4[4], k4[4];
 #pragma unroll
                             for (int u = 0; u < 4; u++) { t4[u] = ROLL_DEAD; if (q0 + 32 * u < n) t4[u] = ent[i0 + q0 + 32 * u]; }
 #pragma unroll
-                            for (int u = 0; u < 4; u++) { c4[u] = ROLL_DEAD; if (t4[u] != ROLL_DEAD) c4[u] = cost[rowoff + (t4[u] >> 16)]; }
+                            for (int u = 0; u < 4; u++) {
+                                c4[u] = ROLL_DEAD; k4[u] = ROLL_DEAD;
+                                if (t4[u] != ROLL_DEAD) { c4[u] = cost[rowoff + (t4[u] >> 16)]; k4[u] = key[t4[u] & 0xFFFF]; }
+                            }
 #pragma unroll
-                            for (int u = 0; u < 4; u++) if (c4[u] <= cst && t4[u] != ROLL_DEAD) {
-                                const uint32_t k2 = key[t4[u] & 0xFFFF];
-                                if (c4[u] < cst || k2 < bkey) { cst = c4[u]; bkey = k2; ex = t4[u]; idx = q0 + 32 * u; }
+                            for (int u = 0; u < 4; u++) {
+                                const unsigned long long pk = ((unsigned long long)c4[u] << 32) | k4[u];
+                                if (pk < best) { best = pk; ex = t4[u]; idx = q0 + 32 * u; }
                             }
                         }
+                        cst = (uint32_t)(best >> 32); bkey = (uint32_t)best;
                     }
                     if (lane == 0) t_look += (unsigned)live;
                     const uint32_t mn = __reduce_min_sync(FULL, cst);
@@ -382,7 +420,7 @@ rollout_local_kernel(DevParams P, int k0, int nticks)
                     if (!small) __syncwarp();
                     live--;
                 }
-                if (lane == 0) icnt[(base + t) * NW + w] = (uint32_t)live;   // len(IdleVehicles) after the match phase
+                if (lane == 0) icnt[c] = (uint32_t)live;                     // len(IdleVehicles) after the match phase
             }
         }
         a_match += t_match; a_val += t_val; a_wait += t_wait; a_look += t_look;
