@@ -344,7 +344,8 @@ def main():
             evs.append((a, b))
         torch.cuda.synchronize(dev)
         kt = {"rollout": float(np.mean([a.elapsed_time(b) for a, b in evs]))}          # ms per launch
-        dom, kname, launches_per_episode = "rollout", "rollout_local_kernel<%d>" % eng.rollout_threads, 1
+        dom, launches_per_episode = "rollout", 1
+        kname = "rollout_local_kernel<%d,%s>" % (eng.rollout_threads, "search" if (w["ncs"] and city.depth_limit > 0) else "local")
     else:
         names = ("update", "match", "supply")
         evs = {n: [] for n in names}
@@ -386,7 +387,8 @@ def main():
         cpu = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
                "sample": f"first {S} replicas x {T} ticks x {rounds} rounds ({wall:.1f} s), C port of the reference loop, {cores} threads"}
         got = eng.stats().cpu().numpy()
-        parity = all(tuple(got[r][:9]) == tuple(oracles[r].stats()[:9]) for r in range(S)) and \
+        keep = [0, 1, 2, 3, 4, 5, 7, 8] if (w["ncs"] and city.depth_limit > 0) else list(range(9))   # search path: own lookup count
+        parity = all(tuple(got[r][keep]) == tuple(np.asarray(oracles[r].stats())[keep]) for r in range(S)) and \
             all(np.array_equal(eng.order_results(r)[0], oracles[r].order_vehicle()) for r in range(min(S, 4)))
 
     if rank == 0:

@@ -43,6 +43,75 @@ def test_fused_rollout_vs_oracle(cuda_device, V, n_orders, windows):
     rollout_vs_oracle(e, [make_oracle(city, V, minute, pick, drop) for _ in range(2)], loc0, windows)
 
 
+@pytest.mark.parametrize("service,V,n_orders,windows", [
+    (1600, 200, 5000, None),           # depth 1, starved: most orders search and reject
+    (2800, 400, 5000, [2, 1, 0]),      # depth 3, window boundaries
+    (2800, 1500, 5000, None),          # depth 3, plenty of idle vehicles: own-cluster matches dominate
+    (2800, 6000, 8000, None),          # depth 3, 256-thread CTAs (84 KB of shared memory per replica)
+])
+def test_fused_search_rollout_vs_oracle(cuda_device, service, V, n_orders, windows):
+    """speculative in-order neighbour search (csrc/rollout.cuh, SEARCH variant) vs the oracle's recursive DFS"""
+    rng = np.random.default_rng(service + V)
+    city = _city(service=service, ncs=True)
+    minute, pick, drop = random_orders(city, n_orders, rng)
+    loc0 = rng.choice(city.valid_nodes(), (2, V)).astype(np.int32)
+    e = _engine(city, V, minute, pick, drop, R=2, trace=True)
+    assert e.fused
+    if windows:
+        windows = list(windows)
+        windows[-1] = e.T - sum(windows)
+    rollout_vs_oracle(e, [make_oracle(city, V, minute, pick, drop) for _ in range(2)], loc0, windows)
+
+
+def test_fused_search_contention(cuda_device):
+    """all pickups in one cluster with NO idle vehicle: every order searches the same neighbour list, so almost
+    every speculative pick inside a chunk collides with the previous order's (the re-evaluation path)."""
+    rng = np.random.default_rng(4)
+    city = _city(service=1600, ncs=True)
+    V = 500
+    sizes = [len(n) for n in city.cluster_nodes]
+    hot = int(np.argmax(sizes))
+    minute, _, drop = random_orders(city, 3000, rng)
+    pick = rng.choice(city.cluster_nodes[hot], len(minute)).astype(np.int32)
+    others = np.concatenate([city.cluster_nodes[int(c)] for c in city.neighbors(hot)])
+    loc0 = rng.choice(others, V).astype(np.int32)
+    e = _engine(city, V, minute, pick, drop, trace=True)
+    rollout_vs_oracle(e, [make_oracle(city, V, minute, pick, drop)], loc0)
+
+
+def test_fused_search_threshold(cuda_device):
+    rng = np.random.default_rng(6)
+    city = _city(service=2800, ncs=True)
+    V = 400
+    minute, pick, drop = random_orders(city, 4000, rng)
+    loc0 = rng.choice(city.valid_nodes(), V).astype(np.int32)
+    for thr in (10, 4):
+        e = _engine(city, V, minute, pick, drop, reject_threshold=thr, trace=True)
+        rollout_vs_oracle(e, [make_oracle(city, V, minute, pick, drop, threshold=thr)], loc0)
+        e.close()
+
+
+def test_fused_search_equals_per_phase_state(cuda_device):
+    rng = np.random.default_rng(22)
+    city = _city(service=2800, ncs=True)
+    V, R = 777, 3
+    minute, pick, drop = random_orders(city, 6000, rng)
+    loc0 = rng.choice(city.valid_nodes(), (R, V)).astype(np.int32)
+    a = _engine(city, V, minute, pick, drop, R=R)
+    b = _engine(city, V, minute, pick, drop, R=R)
+    a.reset(loc0); b.reset(loc0)
+    for k0, n in ((0, 5), (5, 1), (6, a.T - 6)):
+        a.rollout(k0, n)
+        for k in range(k0, k0 + n):
+            b.update(k); b.match(k); b.supply_expect(k)
+        for name in ("veh_loc", "veh_cluster", "veh_arrive", "veh_dest", "veh_key", "order_res",
+                     "per_match", "per_dispatch", "idle_live", "supply", "n_orders"):
+            assert bool((a.tensors[name] == b.tensors[name]).all()), f"{name} differs after tick {k0 + n - 1}"
+    sa, sb = a.stats(), b.stats()
+    keep = [0, 1, 2, 3, 4, 5, 7, 8, 9]
+    assert bool((sa[:, keep] == sb[:, keep]).all())
+
+
 def test_fused_rollout_single_hot_cluster(cuda_device):
     """every vehicle and every pickup in ONE cluster: idle list of V entries, long sequential chain, ties."""
     rng = np.random.default_rng(2)
@@ -102,7 +171,7 @@ def test_fused_tick_with_dispatch_lockstep(cuda_device, ncs):
     lockstep(e, [make_oracle(city, V, minute, pick, drop) for _ in range(2)], loc0, dispatch=True, fused=True)
 
 
-@pytest.mark.parametrize("name", [n for n in SMALL_CASES if n in ("grid_d0",)])
+@pytest.mark.parametrize("name", [n for n in SMALL_CASES if "dispatch" not in n])
 def test_fused_rollout_golden(cuda_device, name):
     """fused rollout vs the trace recorded from the unmodified Python reference."""
     z = load_golden(name)
@@ -123,9 +192,10 @@ def test_fused_rollout_golden(cuda_device, name):
     assert tuple(st[0][:6]) == tuple(z["tr_final"][:6])
 
 
-def test_fused_rollout_real_day(cuda_device):
-    """Shipped 2016-11-01 day, Kmeans-192 / 2000 vehicles (BASELINE configs[0]) if the fixture is present."""
-    z = load_golden("kmeans", real=True)
+@pytest.mark.parametrize("case", ["kmeans", "grid5000d3"])
+def test_fused_rollout_real_day(cuda_device, case):
+    """Shipped 2016-11-01 day (Kmeans-192 / 2000 vehicles = BASELINE configs[0]; Grid / 5000 / depth 3) if present."""
+    z = load_golden(case, real=True)
     if z is None:
         pytest.skip("tests/golden/_real not present (generated by make_golden.py --real)")
     city, V, p = golden_city(z)

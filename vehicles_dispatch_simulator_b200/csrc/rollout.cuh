@@ -55,6 +55,7 @@ __host__ __device__ inline RollLayout roll_layout(int Vp, int C)
     L.wl_cnt = o; o += 16;
     L.wl = o;     o += 2 * Cp;
     L.wl_ix = o;  o += 2 * Cp;
+    if (o - L.wl_pd < 6 * 128) o = L.wl_pd + 6 * 128;        // search variant: 6 x u32[32] speculation records alias this region
     L.total = (o + 15) & ~15;
     return L;
 }
@@ -161,7 +162,66 @@ __device__ __noinline__ uint4 roll_lane_match(RollLane q, RollCommit cm, int m_l
     return st;
 }
 
-template <int THREADS, int MINB>
+// ---- neighbour-search variant (NeighborCanServer, depth >= 1) -------------------------------------------
+// Winner of ONE order against the CURRENT shared-memory state, computed by a whole warp: the order's own
+// cluster if it has an idle vehicle (simulator.py:921-934), else the clusters of the precomputed DFS
+// pre-order list in list order (:936-940, 978-996).  Result is warp-uniform.
+struct RollPick { uint32_t ex, mn, idx, src, look; };     // ex == ROLL_DEAD: no idle vehicle anywhere in reach
+__device__ __forceinline__ RollPick roll_search_pick(const uint32_t *ent, const uint32_t *key, const uint32_t *icnt,
+                                                     const uint32_t *ioff, const uint8_t *__restrict__ cost,
+                                                     const int *__restrict__ soff, const uint16_t *__restrict__ sidx,
+                                                     uint32_t rowoff, int c, int ncs, int lane)
+{
+    uint32_t cst = ROLL_DEAD, ex = ROLL_DEAD, bkey = ROLL_DEAD, idx = 0, bcl = 0, look = 0;
+    int bsp = 0x7FFFFFFF;
+    auto scan = [&](int cs, int spos) {
+        const int i0 = cs ? (int)ioff[cs - 1] : 0, nn = (int)ioff[cs] - i0;      // slots incl. tombstones
+        for (int q = lane; q < nn; q += 32) {
+            const uint32_t t = ent[i0 + q];
+            if (t != ROLL_DEAD) {
+                const uint32_t c2 = cost[rowoff + (t >> 16)];
+                if (c2 < cst || (c2 == cst && spos == bsp)) {
+                    const uint32_t k2 = key[t & 0xFFFF];
+                    if (c2 < cst || k2 < bkey) { cst = c2; bkey = k2; ex = t; idx = (uint32_t)(i0 + q); bsp = spos; bcl = (uint32_t)cs; }
+                }
+            }
+        }
+    };
+    const uint32_t own = icnt[c];
+    if (own > 0) {
+        scan(c, 0); look = own;
+    } else if (ncs) {
+        const int s0 = soff[c], s1 = soff[c + 1];
+        for (int sb = s0 + 1; sb < s1; sb += 32) {                                // position 0 is c itself (empty)
+            const int cl = sb + lane < s1 ? (int)sidx[sb + lane] : -1;
+            const uint32_t lv = cl >= 0 ? icnt[cl] : 0;
+            unsigned nonempty = __ballot_sync(FULL, lv > 0);
+            look += __reduce_add_sync(FULL, lv);
+            while (nonempty) {
+                const int t = __ffs(nonempty) - 1; nonempty &= nonempty - 1;
+                scan(__shfl_sync(FULL, cl, t), sb + t - s0);
+            }
+        }
+    }
+    RollPick r; r.look = look;
+    const uint32_t mn = __reduce_min_sync(FULL, cst);
+    r.mn = mn;
+    if (mn == ROLL_DEAD) { r.ex = ROLL_DEAD; r.idx = 0; r.src = 0; return r; }
+    unsigned tied = __ballot_sync(FULL, cst == mn);
+    if (tied & (tied - 1)) {
+        const uint32_t smin = __reduce_min_sync(FULL, cst == mn ? (uint32_t)bsp : ROLL_DEAD);
+        tied = __ballot_sync(FULL, cst == mn && (uint32_t)bsp == smin);
+        if (tied & (tied - 1)) {
+            const uint32_t kmin = __reduce_min_sync(FULL, (tied >> lane & 1) ? bkey : ROLL_DEAD);
+            tied = __ballot_sync(FULL, (tied >> lane & 1) && bkey == kmin);
+        }
+    }
+    const int win = __ffs(tied) - 1;
+    r.ex = __shfl_sync(FULL, ex, win); r.idx = __shfl_sync(FULL, idx, win); r.src = __shfl_sync(FULL, bcl, win);
+    return r;
+}
+
+template <int THREADS, int MINB, bool SEARCH>
 __global__ void __launch_bounds__(THREADS, MINB)
 rollout_local_kernel(DevParams P, int k0, int nticks)
 {
@@ -321,6 +381,7 @@ rollout_local_kernel(DevParams P, int k0, int nticks)
         RollLane lq;
         lq.ent = ent; lq.key = key; lq.spd_t = spd_t; lq.sidx_t = sidx_t; lq.n2c = n2c; lq.cost = cost;
         lq.nodes_u = nodes_u; lq.thr32 = thr32; lq.no_timeout = no_timeout ? 1 : 0;
+        if constexpr (!SEARCH) {
         // -- 6a: every thread classifies clusters (orders this tick? idle vehicles?) and files the active ones,
         //    first order already fetched: clusters with <= 4 idle vehicles at the back of the work list
         //    (one THREAD each), the others at the front (one WARP each).
@@ -422,6 +483,82 @@ rollout_local_kernel(DevParams P, int k0, int nticks)
                 }
                 if (lane == 0) icnt[c] = (uint32_t)live;                     // len(IdleVehicles) after the match phase
             }
+        }
+        } else {
+        // -- search variant.  Orders are matched strictly in index order (a match may take a vehicle from ANY
+        //    cluster of the search list), but idle sets only SHRINK inside a tick.  So the 32 orders of a chunk
+        //    are first evaluated in parallel (one warp each) against the state at chunk start; an evaluation
+        //    stays exact at the order's turn iff its winner is still idle then (the argmin over a superset that
+        //    survives is the argmin over the subset; an empty own cluster stays empty; "nothing in reach" stays
+        //    so).  Warp 0 then commits in order: all orders up to the first stale one at once, re-evaluates that
+        //    one against the current state, and repeats.
+        uint32_t *sp_ex = wl_pd, *sp_idx = wl_pd + 32, *sp_mn = wl_pd + 64, *sp_src = wl_pd + 96,
+                 *sp_pd = wl_pd + 128, *sp_vd = wl_pd + 160;
+        const uint32_t *opd_t = P.opd + (size_t)ro * P.Nmax + tb;
+        for (int base = 0; base < n_tick; base += 32) {
+            const int cnt = min(32, n_tick - base);
+            {   // speculative evaluation: warp w takes orders w, w + NW, ...
+                uint32_t pd_l = 0; int c_l = 0;
+                if (lane < cnt) { pd_l = opd_t[base + lane]; c_l = n2c[pd_l & 0xFFFF]; }
+                for (int sI = w; sI < cnt; sI += NW) {
+                    const uint32_t o_pd = __shfl_sync(FULL, pd_l, sI);
+                    const int c = __shfl_sync(FULL, c_l, sI);
+                    const unsigned pnode = o_pd & 0xFFFF, dnode = o_pd >> 16;
+                    const uint32_t vd = (uint32_t)cost[dnode * nodes_u + pnode] | ((uint32_t)n2c[dnode] << 16);
+                    const RollPick pk = roll_search_pick(ent, key, icnt, ioff, cost, P.soff, P.sidx, pnode * nodes_u, c, P.ncs, lane);
+                    if (lane == 0) {
+                        sp_ex[sI] = pk.ex; sp_idx[sI] = pk.idx; sp_mn[sI] = pk.mn; sp_src[sI] = pk.src | ((uint32_t)c << 16);
+                        sp_pd[sI] = o_pd; sp_vd[sI] = vd;
+                        t_look += pk.look;
+                    }
+                }
+            }
+            __syncthreads();
+            if (w == 0) {
+                uint32_t ex = ROLL_DEAD, mn = 0, idx = 0, src = 0, o_pd = 0, vd = 0;
+                if (lane < cnt) { ex = sp_ex[lane]; mn = sp_mn[lane]; idx = sp_idx[lane]; src = sp_src[lane]; o_pd = sp_pd[lane]; vd = sp_vd[lane]; }
+                const bool has = ex != ROLL_DEAD;                 // a winner exists (it is taken unless mn > threshold)
+                const bool take = has && mn <= thr32;
+                unsigned pending = __ballot_sync(FULL, lane < cnt);
+                while (pending) {
+                    const bool pend = pending >> lane & 1;
+                    bool ok = true;
+                    if (pend && has) ok = arrive[ex & 0xFFFF] == IDLE16;
+                    const unsigned grp = __match_any_sync(FULL, (pend && has) ? (ex & 0xFFFF) : (0x10000u + lane));
+                    const unsigned takers = __ballot_sync(FULL, pend && take);
+                    if (pend && has && (grp & takers & lanemask_lt())) ok = false;     // an earlier order of the chunk takes it
+                    const unsigned bad = __ballot_sync(FULL, pend && !ok);
+                    const int first = bad ? __ffs(bad) - 1 : 32;
+                    const unsigned go = first == 32 ? pending : (pending & ((1u << first) - 1u));
+                    if ((go >> lane & 1) && take) {
+                        cm.commit(ex, mn, (int)(vd & 0xFFFF), o_pd >> 16, (int)(vd >> 16), base + lane);
+                        ent[idx] = ROLL_DEAD;                                          // IdleVehicles.remove (:963)
+                        atomicSub(&icnt[src & 0xFFFF], 1u);
+                        t_match++; t_wait += mn; t_val += vd & 0xFFFF;
+                    }
+                    pending &= ~go;
+                    __syncwarp();
+                    if (first < 32) {                                                  // stale: evaluate again, now exact
+                        const uint32_t f_pd = __shfl_sync(FULL, o_pd, first), f_vd = __shfl_sync(FULL, vd, first);
+                        const int f_c = (int)(__shfl_sync(FULL, src, first) >> 16);
+                        const RollPick pk = roll_search_pick(ent, key, icnt, ioff, cost, P.soff, P.sidx,
+                                                             (f_pd & 0xFFFF) * nodes_u, f_c, P.ncs, lane);
+                        if (lane == 0) {
+                            t_look += pk.look;
+                            if (pk.ex != ROLL_DEAD && pk.mn <= thr32) {
+                                cm.commit(pk.ex, pk.mn, (int)(f_vd & 0xFFFF), f_pd >> 16, (int)(f_vd >> 16), base + first);
+                                ent[pk.idx] = ROLL_DEAD;
+                                icnt[pk.src] -= 1;
+                                t_match++; t_wait += pk.mn; t_val += f_vd & 0xFFFF;
+                            }
+                        }
+                        pending &= ~(1u << first);
+                        __syncwarp();
+                    }
+                }
+            }
+            __syncthreads();
+        }
         }
         a_match += t_match; a_val += t_val; a_wait += t_wait; a_look += t_look;
         if (tid == 0) { a_orders += n_tick; a_tickval += P.tick_value[(size_t)ro * P.T + k]; }

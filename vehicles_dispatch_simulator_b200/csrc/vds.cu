@@ -733,9 +733,12 @@ int vds_create(const vds_config *cfg, vds_handle *out)
     if (h->roll_smem <= (int)prop.sharedMemPerBlockOptin) {
         const int per_sm = (int)prop.sharedMemPerMultiprocessor / (h->roll_smem + 1024);
         h->roll_threads = per_sm >= 6 ? 128 : per_sm >= 3 ? 256 : 512;
-        CK(cudaFuncSetAttribute(rollout_local_kernel<128, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
-        CK(cudaFuncSetAttribute(rollout_local_kernel<256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
-        CK(cudaFuncSetAttribute(rollout_local_kernel<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
+        CK(cudaFuncSetAttribute(rollout_local_kernel<128, 7, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
+        CK(cudaFuncSetAttribute(rollout_local_kernel<256, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
+        CK(cudaFuncSetAttribute(rollout_local_kernel<512, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
+        CK(cudaFuncSetAttribute(rollout_local_kernel<128, 7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
+        CK(cudaFuncSetAttribute(rollout_local_kernel<256, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
+        CK(cudaFuncSetAttribute(rollout_local_kernel<512, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
     }
     return VDS_OK;
 }
@@ -887,7 +890,7 @@ int vds_dispatch(vds_handle h, int tick, const int32_t *move_off, const int32_t 
 
 int vds_rollout_is_fused(vds_handle h)
 {
-    return h && local_mode(h) && h->prepared && h->roll_threads > 0;
+    return h && h->prepared && h->roll_threads > 0;
 }
 
 int vds_rollout_threads(vds_handle h) { return h ? h->roll_threads : 0; }
@@ -899,10 +902,18 @@ int vds_rollout(vds_handle h, int tick0, int nticks, void *stream)
     if (nticks == 0) return VDS_OK;
     if (vds_rollout_is_fused(h)) {
         cudaStream_t st = (cudaStream_t)stream;
-        switch (h->roll_threads) {
-        case 128: rollout_local_kernel<128, 7><<<h->P.R, 128, h->roll_smem, st>>>(h->P, tick0, nticks); break;
-        case 256: rollout_local_kernel<256, 3><<<h->P.R, 256, h->roll_smem, st>>>(h->P, tick0, nticks); break;
-        default:  rollout_local_kernel<512, 1><<<h->P.R, 512, h->roll_smem, st>>>(h->P, tick0, nticks); break;
+        if (local_mode(h)) {
+            switch (h->roll_threads) {
+            case 128: rollout_local_kernel<128, 7, false><<<h->P.R, 128, h->roll_smem, st>>>(h->P, tick0, nticks); break;
+            case 256: rollout_local_kernel<256, 3, false><<<h->P.R, 256, h->roll_smem, st>>>(h->P, tick0, nticks); break;
+            default:  rollout_local_kernel<512, 1, false><<<h->P.R, 512, h->roll_smem, st>>>(h->P, tick0, nticks); break;
+            }
+        } else {
+            switch (h->roll_threads) {
+            case 128: rollout_local_kernel<128, 7, true><<<h->P.R, 128, h->roll_smem, st>>>(h->P, tick0, nticks); break;
+            case 256: rollout_local_kernel<256, 3, true><<<h->P.R, 256, h->roll_smem, st>>>(h->P, tick0, nticks); break;
+            default:  rollout_local_kernel<512, 1, true><<<h->P.R, 512, h->roll_smem, st>>>(h->P, tick0, nticks); break;
+            }
         }
         CKL("rollout_local_kernel");
         return VDS_OK;
