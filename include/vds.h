@@ -92,6 +92,12 @@ typedef struct vds_static {
     const uint16_t *node2cluster; /* [nodes], 0xFFFF = node outside every cluster (NodeID2Cluseter, :314-322) */
     const int32_t  *search_off;   /* [C+1] CSR offsets into search_idx */
     const uint16_t *search_idx;   /* DFS pre-order of FindServerVehicleFunction (:978-996) per start cluster */
+    /* inverse of the search lists: cluster s is in the search list of every cluster in
+     * reach_idx[reach_off[s] .. reach_off[s+1]) (s itself included).  Lets the match kernels keep, per cluster,
+     * the number of idle vehicles anywhere in its reach and reject an order whose reach is empty in O(1).
+     * May be NULL when neighbor_can_server == 0 or depth_limit == 0. */
+    const int32_t  *reach_off;    /* [C+1] */
+    const uint16_t *reach_idx;
 } vds_static;
 
 /* Orders sorted by release minute (post preprocessing/readfiles.py:70-81). */

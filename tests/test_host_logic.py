@@ -31,6 +31,7 @@ def test_c_abi_exports_every_declared_symbol():
     assert ctypes.sizeof(_native.Config) == 12 * 4 + 8
     assert ctypes.sizeof(_native.State) == 18 * 8
     assert ctypes.sizeof(_native.Orders) == 8 * 8
+    assert ctypes.sizeof(_native.Static) == 6 * 8
 
 
 def test_no_cpu_fallback_without_gpu():

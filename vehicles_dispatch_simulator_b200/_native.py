@@ -36,7 +36,8 @@ class Config(C.Structure):
 
 
 class Static(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("cost_u8", "node2cluster", "search_off", "search_idx")]
+    _fields_ = [(n, C.c_void_p) for n in ("cost_u8", "node2cluster", "search_off", "search_idx",
+                                          "reach_off", "reach_idx")]
 
 
 class Orders(C.Structure):

@@ -167,57 +167,85 @@ __device__ __noinline__ uint4 roll_lane_match(RollLane q, RollCommit cm, int m_l
 // cluster if it has an idle vehicle (simulator.py:921-934), else the clusters of the precomputed DFS
 // pre-order list in list order (:936-940, 978-996).  Result is warp-uniform.
 struct RollPick { uint32_t ex, mn, idx, src, look; };     // ex == ROLL_DEAD: no idle vehicle anywhere in reach
+// per-lane running best of a scan: (cost << 16 | search position) and idle key, compared lexicographically
+struct RollBest {
+    unsigned long long pk; uint32_t ex, idx;
+    __device__ __forceinline__ void offer(uint32_t t, uint32_t c2, uint32_t spos, uint32_t k2, uint32_t where) {
+        const unsigned long long v = ((unsigned long long)((c2 << 16) | spos) << 32) | k2;
+        if (v < pk) { pk = v; ex = t; idx = where; }
+    }
+};
 __device__ __forceinline__ RollPick roll_search_pick(const uint32_t *ent, const uint32_t *key, const uint32_t *icnt,
                                                      const uint32_t *ioff, const uint8_t *__restrict__ cost,
                                                      const int *__restrict__ soff, const uint16_t *__restrict__ sidx,
                                                      uint32_t rowoff, int c, int ncs, int lane)
 {
-    uint32_t cst = ROLL_DEAD, ex = ROLL_DEAD, bkey = ROLL_DEAD, idx = 0, bcl = 0, look = 0;
-    int bsp = 0x7FFFFFFF;
-    auto scan = [&](int cs, int spos) {
-        const int i0 = cs ? (int)ioff[cs - 1] : 0, nn = (int)ioff[cs] - i0;      // slots incl. tombstones
-        for (int q = lane; q < nn; q += 32) {
-            const uint32_t t = ent[i0 + q];
-            if (t != ROLL_DEAD) {
-                const uint32_t c2 = cost[rowoff + (t >> 16)];
-                if (c2 < cst || (c2 == cst && spos == bsp)) {
-                    const uint32_t k2 = key[t & 0xFFFF];
-                    if (c2 < cst || k2 < bkey) { cst = c2; bkey = k2; ex = t; idx = (uint32_t)(i0 + q); bsp = spos; bcl = (uint32_t)cs; }
-                }
-            }
-        }
-    };
+    RollBest b; b.pk = ~0ull; b.ex = ROLL_DEAD; b.idx = 0;
+    uint32_t look = 0;
     const uint32_t own = icnt[c];
     if (own > 0) {
-        scan(c, 0); look = own;
+        // own cluster: lanes over its slots, 2 independent gathers in flight
+        const int i0 = c ? (int)ioff[c - 1] : 0, nn = (int)ioff[c] - i0;          // slots incl. tombstones
+        for (int q0 = lane; q0 < nn; q0 += 64) {
+            uint32_t t2[2], c2[2], k2[2];
+#pragma unroll
+            for (int u = 0; u < 2; u++) { t2[u] = ROLL_DEAD; if (q0 + 32 * u < nn) t2[u] = ent[i0 + q0 + 32 * u]; }
+#pragma unroll
+            for (int u = 0; u < 2; u++) if (t2[u] != ROLL_DEAD) { c2[u] = cost[rowoff + (t2[u] >> 16)]; k2[u] = key[t2[u] & 0xFFFF]; }
+#pragma unroll
+            for (int u = 0; u < 2; u++) if (t2[u] != ROLL_DEAD) b.offer(t2[u], c2[u], 0, k2[u], (uint32_t)(i0 + q0 + 32 * u));
+        }
+        look = own;
     } else if (ncs) {
+        // neighbour search: the slots of up to 32 clusters of the search list are FLATTENED over the lanes
+        // (prefix sum of the list lengths + a 5-step shuffle binary search per candidate), so every cost
+        // gather of the order is in flight at once instead of one cluster after the other.
         const int s0 = soff[c], s1 = soff[c + 1];
         for (int sb = s0 + 1; sb < s1; sb += 32) {                                // position 0 is c itself (empty)
             const int cl = sb + lane < s1 ? (int)sidx[sb + lane] : -1;
             const uint32_t lv = cl >= 0 ? icnt[cl] : 0;
-            unsigned nonempty = __ballot_sync(FULL, lv > 0);
+            int i0 = 0, nn = 0;
+            if (lv > 0) { i0 = cl ? (int)ioff[cl - 1] : 0; nn = (int)ioff[cl] - i0; }
             look += __reduce_add_sync(FULL, lv);
-            while (nonempty) {
-                const int t = __ffs(nonempty) - 1; nonempty &= nonempty - 1;
-                scan(__shfl_sync(FULL, cl, t), sb + t - s0);
+            int incl = nn;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += t; }
+            const int total = __shfl_sync(FULL, incl, 31);
+            for (int j0 = 0; j0 < total; j0 += 64) {
+                uint32_t t2[2], c2[2], k2[2], sp[2], wh[2];
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    const int j = j0 + 32 * u + lane;
+                    int pos = 0;                                                   // smallest pos with incl[pos] > j
+#pragma unroll
+                    for (int st = 16; st; st >>= 1) { const int v = __shfl_sync(FULL, incl, pos + st - 1); if (v <= j) pos += st; }
+                    pos = min(pos, 31);
+                    const int excl = __shfl_sync(FULL, incl, pos) - __shfl_sync(FULL, nn, pos);
+                    const int base_i0 = __shfl_sync(FULL, i0, pos);
+                    t2[u] = ROLL_DEAD; sp[u] = (uint32_t)(sb + pos - s0); wh[u] = (uint32_t)(base_i0 + (j - excl));
+                    if (j < total) t2[u] = ent[wh[u]];
+                }
+#pragma unroll
+                for (int u = 0; u < 2; u++) if (t2[u] != ROLL_DEAD) { c2[u] = cost[rowoff + (t2[u] >> 16)]; k2[u] = key[t2[u] & 0xFFFF]; }
+#pragma unroll
+                for (int u = 0; u < 2; u++) if (t2[u] != ROLL_DEAD) b.offer(t2[u], c2[u], sp[u], k2[u], wh[u]);
             }
         }
     }
     RollPick r; r.look = look;
-    const uint32_t mn = __reduce_min_sync(FULL, cst);
-    r.mn = mn;
-    if (mn == ROLL_DEAD) { r.ex = ROLL_DEAD; r.idx = 0; r.src = 0; return r; }
-    unsigned tied = __ballot_sync(FULL, cst == mn);
-    if (tied & (tied - 1)) {
-        const uint32_t smin = __reduce_min_sync(FULL, cst == mn ? (uint32_t)bsp : ROLL_DEAD);
-        tied = __ballot_sync(FULL, cst == mn && (uint32_t)bsp == smin);
-        if (tied & (tied - 1)) {
-            const uint32_t kmin = __reduce_min_sync(FULL, (tied >> lane & 1) ? bkey : ROLL_DEAD);
-            tied = __ballot_sync(FULL, (tied >> lane & 1) && bkey == kmin);
-        }
+    const uint32_t hi = (uint32_t)(b.pk >> 32), lo = (uint32_t)b.pk;
+    const uint32_t hmin = __reduce_min_sync(FULL, hi);                         // (cost, search position)
+    if (hmin == ROLL_DEAD) { r.ex = ROLL_DEAD; r.mn = ROLL_DEAD; r.idx = 0; r.src = 0; return r; }
+    unsigned tied = __ballot_sync(FULL, hi == hmin);
+    if (tied & (tied - 1)) {                                                    // same cluster, same cost: idle-list order (Q5)
+        const uint32_t kmin = __reduce_min_sync(FULL, hi == hmin ? lo : ROLL_DEAD);
+        tied = __ballot_sync(FULL, hi == hmin && lo == kmin);
     }
     const int win = __ffs(tied) - 1;
-    r.ex = __shfl_sync(FULL, ex, win); r.idx = __shfl_sync(FULL, idx, win); r.src = __shfl_sync(FULL, bcl, win);
+    r.mn = hmin >> 16;
+    r.ex = __shfl_sync(FULL, b.ex, win); r.idx = __shfl_sync(FULL, b.idx, win);
+    const uint32_t spos = hmin & 0xFFFF;
+    r.src = spos ? (uint32_t)sidx[soff[c] + spos] : (uint32_t)c;
     return r;
 }
 

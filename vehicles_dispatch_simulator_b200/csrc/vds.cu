@@ -30,6 +30,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <new>
 
 #define IDLE16 0xFFFFu
@@ -41,7 +42,7 @@
 struct DevParams {
     int R, V, Vp, C, nodes, Nmax, T, period, depth, ncs, OR, maxOT; unsigned period_magic;
     long long threshold;
-    const uint8_t *cost; const uint16_t *n2c; const int *soff; const uint16_t *sidx;
+    const uint8_t *cost; const uint16_t *n2c; const int *soff; const uint16_t *sidx; const int *roff; const uint16_t *ridx;
     const uint32_t *opd; const uint8_t *oval; const int *toff; const long long *vtotal;
     uint16_t *veh_loc, *veh_cluster, *veh_arrive, *veh_dest; uint32_t *veh_key;
     uint32_t *order_res; int *per_match, *per_dispatch, *idle_live, *supply, *n_orders;
@@ -53,7 +54,7 @@ struct DevParams {
 struct vds_handle_s {
     vds_config cfg;
     DevParams P;
-    bool have_static, have_orders, have_state, have_sorted, prepared;
+    bool have_static, have_orders, have_state, have_sorted, prepared, fused_search;
     int roll_threads, roll_smem;
     char err[512];
     int64_t launches;
@@ -363,13 +364,21 @@ match_search_kernel(DevParams P, int k)
     const int r = blockIdx.x * MS_WARPS + w;
     if (r >= P.R) return;
     const int C = P.C;
-    int *ioff = sm + w * (2 * C + 2);       // [C+1]
+    int *ioff = sm + w * (3 * C + 2);       // [C+1]
     int *live = ioff + C + 1;               // [C]
+    int *reach = live + C;                  // [C] idle vehicles anywhere in the cluster's search list
     {
         const int *g_off = P.idle_off + (size_t)r * (C + 1);
         const int *g_lv = P.idle_live + (size_t)r * C;
         for (int i = lane; i <= C; i += 32) ioff[i] = g_off[i];
         for (int i = lane; i < C; i += 32) live[i] = g_lv[i];
+    }
+    __syncwarp();
+    for (int i = lane; i < C; i += 32) {
+        int s = 0;
+        if (P.ncs) for (int q = P.soff[i]; q < P.soff[i + 1]; q++) s += live[P.sidx[q]];
+        else s = live[i];
+        reach[i] = s;
     }
     __syncwarp();
     const int ro = P.OR == 1 ? 0 : r;
@@ -387,52 +396,88 @@ match_search_kernel(DevParams P, int k)
         uint32_t pd = 0; int val = 0, oc = 0;
         if (base + lane < n) { pd = opd[base + lane]; val = oval[base + lane]; oc = P.n2c[pd & 0xFFFF]; }
         const int cnt = min(32, n - base);
-        for (int j = 0; j < cnt; j++) {
+        // an order with no idle vehicle anywhere in its reach is rejected now and for the rest of the tick
+        // (idle sets only shrink inside a tick): settle all of those of the chunk at once
+        const bool dead_l = lane < cnt && reach[oc] == 0;
+        unsigned todo = __ballot_sync(FULL, lane < cnt && !dead_l);
+        if (dead_l) res[base + lane] = 0x0000FFFFu;
+        rej += __popc(__ballot_sync(FULL, dead_l)); rejval += __reduce_add_sync(FULL, dead_l ? val : 0);
+        while (todo) {
+            const int j = __ffs(todo) - 1; todo &= todo - 1;
             const uint32_t o_pd = __shfl_sync(FULL, pd, j);
             const int o_val = __shfl_sync(FULL, val, j);
             const int c = __shfl_sync(FULL, oc, j);
-            const uint8_t *row = P.cost + (size_t)(o_pd & 0xFFFF) * P.nodes;
-            uint32_t cst = DEAD32, key = DEAD32, ex = DEAD32; int idx = 0, bsp = 0x7FFFFFFF, bcl = 0;
-            auto scan = [&](int cs, int spos) {
-                const int i0 = ioff[cs], nn = ioff[cs + 1] - i0;
-                for (int q = lane; q < nn; q += 32) {
-                    uint2 t = ent[i0 + q];
-                    if (t.x != DEAD32) {
-                        uint32_t c2 = row[t.x >> 16]; my_lookups++;
-                        if (c2 < cst || (c2 == cst && spos == bsp && t.y < key)) { cst = c2; key = t.y; ex = t.x; idx = i0 + q; bsp = spos; bcl = cs; }
-                    }
-                }
+            const uint32_t rowoff = (o_pd & 0xFFFF) * (uint32_t)P.nodes;        // RoadCost(loc, pickup) = cost[pickup][loc]
+            // per-lane running best: (cost << 16 | search position) then idle key, lexicographic
+            unsigned long long best = ~0ull; uint32_t ex = DEAD32; int idx = 0;
+            auto offer = [&](uint2 t, uint32_t c2, uint32_t spos, int where) {
+                const unsigned long long v = ((unsigned long long)((c2 << 16) | spos) << 32) | t.y;
+                if (v < best) { best = v; ex = t.x; idx = where; }
             };
             if (live[c] > 0) {
-                scan(c, 0);
+                const int i0 = ioff[c], nn = ioff[c + 1] - i0;
+                for (int q0 = lane; q0 < nn; q0 += 64) {                          // 2 independent gathers in flight
+                    uint2 t2[2]; uint32_t c2[2];
+#pragma unroll
+                    for (int u = 0; u < 2; u++) { t2[u] = make_uint2(DEAD32, DEAD32); if (q0 + 32 * u < nn) t2[u] = ent[i0 + q0 + 32 * u]; }
+#pragma unroll
+                    for (int u = 0; u < 2; u++) if (t2[u].x != DEAD32) c2[u] = P.cost[rowoff + (t2[u].x >> 16)];
+#pragma unroll
+                    for (int u = 0; u < 2; u++) if (t2[u].x != DEAD32) offer(t2[u], c2[u], 0, i0 + q0 + 32 * u);
+                }
+                my_lookups += lane == 0 ? live[c] : 0;
             } else if (P.ncs) {
+                // the idle slots of up to 32 clusters of the DFS pre-order list are FLATTENED over the lanes
+                // (prefix sum of list lengths + shuffle binary search), so all cost gathers of the order are in
+                // flight at once instead of cluster after cluster
                 const int s0 = P.soff[c], s1 = P.soff[c + 1];
-                for (int sb = s0 + 1; sb < s1; sb += 32) {          // position 0 is c itself (empty)
-                    int cl = sb + lane < s1 ? (int)P.sidx[sb + lane] : -1;
-                    unsigned nonempty = __ballot_sync(FULL, cl >= 0 && live[cl] > 0);
-                    while (nonempty) {
-                        const int t = __ffs(nonempty) - 1; nonempty &= nonempty - 1;
-                        scan(__shfl_sync(FULL, cl, t), sb + t - s0);
+                for (int sb = s0 + 1; sb < s1; sb += 32) {                        // position 0 is c itself (empty)
+                    const int cl = sb + lane < s1 ? (int)P.sidx[sb + lane] : -1;
+                    const int lv = cl >= 0 ? live[cl] : 0;
+                    int i0 = 0, nn = 0;
+                    if (lv > 0) { i0 = ioff[cl]; nn = ioff[cl + 1] - i0; }
+                    my_lookups += lv;
+                    int incl = nn;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += t; }
+                    const int total = __shfl_sync(FULL, incl, 31);
+                    for (int j0 = 0; j0 < total; j0 += 64) {
+                        uint2 t2[2]; uint32_t c2[2], sp[2]; int wh[2];
+#pragma unroll
+                        for (int u = 0; u < 2; u++) {
+                            const int jj = j0 + 32 * u + lane;
+                            int pos = 0;                                           // smallest pos with incl[pos] > jj
+#pragma unroll
+                            for (int st = 16; st; st >>= 1) { const int v = __shfl_sync(FULL, incl, pos + st - 1); if (v <= jj) pos += st; }
+                            pos = min(pos, 31);
+                            const int excl = __shfl_sync(FULL, incl, pos) - __shfl_sync(FULL, nn, pos);
+                            const int base_i0 = __shfl_sync(FULL, i0, pos);
+                            t2[u] = make_uint2(DEAD32, DEAD32); sp[u] = (uint32_t)(sb + pos - s0); wh[u] = base_i0 + (jj - excl);
+                            if (jj < total) t2[u] = ent[wh[u]];
+                        }
+#pragma unroll
+                        for (int u = 0; u < 2; u++) if (t2[u].x != DEAD32) c2[u] = P.cost[rowoff + (t2[u].x >> 16)];
+#pragma unroll
+                        for (int u = 0; u < 2; u++) if (t2[u].x != DEAD32) offer(t2[u], c2[u], sp[u], wh[u]);
                     }
                 }
             }
-            const uint32_t mn = __reduce_min_sync(FULL, cst);
+            const uint32_t hi = (uint32_t)(best >> 32), lo = (uint32_t)best;
+            const uint32_t hmin = __reduce_min_sync(FULL, hi);                     // (cost, search position)
+            const uint32_t mn = hmin == DEAD32 ? DEAD32 : hmin >> 16;
             if (mn == DEAD32 || (long long)mn > P.threshold) {
                 if (lane == 0) res[base + j] = 0x0000FFFFu;
                 rej++; rejval += o_val;
                 continue;
             }
-            unsigned tied = __ballot_sync(FULL, cst == mn);
-            if (__popc(tied) > 1) {
-                const uint32_t smin = __reduce_min_sync(FULL, cst == mn ? (uint32_t)bsp : DEAD32);
-                tied = __ballot_sync(FULL, cst == mn && (uint32_t)bsp == smin);
-                if (__popc(tied) > 1) {
-                    const uint32_t kmin = __reduce_min_sync(FULL, (tied >> lane & 1) ? key : DEAD32);
-                    tied = __ballot_sync(FULL, (tied >> lane & 1) && key == kmin);
-                }
+            unsigned tied = __ballot_sync(FULL, hi == hmin);
+            if (tied & (tied - 1)) {                                                // same cluster, same cost: idle-list order (Q5)
+                const uint32_t kmin = __reduce_min_sync(FULL, hi == hmin ? lo : DEAD32);
+                tied = __ballot_sync(FULL, hi == hmin && lo == kmin);
             }
             const int win = __ffs(tied) - 1;
-            const int src = __shfl_sync(FULL, bcl, win);
+            const uint32_t spos = hmin & 0xFFFF;
+            const int src = spos ? (int)P.sidx[P.soff[c] + spos] : c;
             if (lane == win) {
                 const int v = ex & 0xFFFF;
                 int d = ((int)mn + o_val + P.period - 1) / P.period; if (d < 1) d = 1;
@@ -445,6 +490,7 @@ match_search_kernel(DevParams P, int k)
                 ent[idx].x = DEAD32;
                 live[src] -= 1;
             }
+            for (int q = P.roff[src] + lane; q < P.roff[src + 1]; q += 32) reach[P.ridx[q]] -= 1;
             __syncwarp();
             matches++; wait_sum += mn;
         }
@@ -669,6 +715,7 @@ __global__ void gen_placement_kernel(DevParams P, uint64_t seed, long long first
 }
 
 // =========================================================== host-side C ABI
+static bool local_mode(const vds_handle h) { return !(h->P.ncs && h->P.depth > 0); }
 static int fail(vds_handle h, int code, const char *msg)
 {
     if (h) snprintf(h->err, sizeof(h->err), "%s", msg);
@@ -727,6 +774,7 @@ int vds_create(const vds_config *cfg, vds_handle *out)
     CK(cudaFuncSetAttribute(update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, upd_smem));
     const int prep_smem = (int)sizeof(int) * (2 * Cp + 4 + 16 + PREP_WARPS * Cp);
     CK(cudaFuncSetAttribute(prepare_orders_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, prep_smem));
+    { const char *e = getenv("VDS_FUSED_SEARCH"); h->fused_search = e && e[0] == '1'; }
     // replica-resident rollout kernel: pick the CTA width from how many replicas fit one SM
     h->roll_smem = roll_layout(P.Vp, P.C).total;
     h->roll_threads = 0;
@@ -751,6 +799,9 @@ int vds_bind_static(vds_handle h, const vds_static *s)
     if (!h || !s || !s->cost_u8 || !s->node2cluster || !s->search_off || !s->search_idx)
         return fail(h, VDS_ERR_INVALID, "vds_bind_static: null pointer");
     h->P.cost = s->cost_u8; h->P.n2c = s->node2cluster; h->P.soff = s->search_off; h->P.sidx = s->search_idx;
+    h->P.roff = s->reach_off; h->P.ridx = s->reach_idx;
+    if (!local_mode(h) && (!s->reach_off || !s->reach_idx))
+        return fail(h, VDS_ERR_INVALID, "vds_bind_static: reach_off / reach_idx are required with neighbour search");
     h->have_static = true; return VDS_OK;
 }
 int vds_bind_orders(vds_handle h, const vds_orders *o)
@@ -789,8 +840,6 @@ static int ready(vds_handle h, bool need_orders)
         return fail(h, VDS_ERR_UNBOUND, "vds: bind_static / bind_orders / bind_state must be called first");
     return VDS_OK;
 }
-static bool local_mode(const vds_handle h) { return !(h->P.ncs && h->P.depth > 0); }
-
 int vds_compute_order_values(vds_handle h, const uint32_t *order_pd, const int32_t *n_orders,
                              uint8_t *order_value, int64_t *value_total, void *stream)
 {
@@ -861,7 +910,7 @@ int vds_match(vds_handle h, int tick, void *stream)
         match_local_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(P, tick);
         CKL("match_local_kernel");
     } else {
-        const int smem = (int)sizeof(int) * MS_WARPS * (2 * P.C + 2);
+        const int smem = (int)sizeof(int) * MS_WARPS * (3 * P.C + 2);
         match_search_kernel<<<(P.R + MS_WARPS - 1) / MS_WARPS, MS_WARPS * 32, smem, (cudaStream_t)stream>>>(P, tick);
         CKL("match_search_kernel");
     }
@@ -890,7 +939,7 @@ int vds_dispatch(vds_handle h, int tick, const int32_t *move_off, const int32_t 
 
 int vds_rollout_is_fused(vds_handle h)
 {
-    return h && h->prepared && h->roll_threads > 0;
+    return h && h->prepared && h->roll_threads > 0 && (local_mode(h) || h->fused_search);
 }
 
 int vds_rollout_threads(vds_handle h) { return h ? h->roll_threads : 0; }

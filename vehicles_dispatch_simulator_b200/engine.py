@@ -76,6 +76,17 @@ class City:
             self._search = (np.array(off, np.int32), np.array(idx, np.uint16))
         return self._search
 
+    def reach_lists(self):
+        """Inverse of search_lists(): for every cluster s the clusters whose search list contains s."""
+        soff, sidx = self.search_lists()
+        inv = [[] for _ in range(self.n_clusters)]
+        for c in range(self.n_clusters):
+            for s in sidx[soff[c]:soff[c + 1]]:
+                inv[int(s)].append(c)
+        off = np.cumsum([0] + [len(x) for x in inv]).astype(np.int32)
+        idx = np.array([c for x in inv for c in x], np.uint16)
+        return off, idx
+
     def valid_nodes(self):
         return np.nonzero(self.node2cluster >= 0)[0].astype(np.uint16)
 
@@ -133,7 +144,11 @@ class DispatchEngine:
             self.t_n2c = torch.from_numpy(n2c).to(dev)
             self.t_soff = torch.from_numpy(soff).to(dev)
             self.t_sidx = torch.from_numpy(sidx if len(sidx) else np.zeros(1, np.uint16)).to(dev)
-            st = N.Static(self.t_cost.data_ptr(), self.t_n2c.data_ptr(), self.t_soff.data_ptr(), self.t_sidx.data_ptr())
+            roff, ridx = city.reach_lists()
+            self.t_roff = torch.from_numpy(roff).to(dev)
+            self.t_ridx = torch.from_numpy(ridx if len(ridx) else np.zeros(1, np.uint16)).to(dev)
+            st = N.Static(self.t_cost.data_ptr(), self.t_n2c.data_ptr(), self.t_soff.data_ptr(), self.t_sidx.data_ptr(),
+                          self.t_roff.data_ptr(), self.t_ridx.data_ptr())
             self._ck(self.L.vds_bind_static(self.h, C.byref(st)))
             # ---- orders
             z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dev)
