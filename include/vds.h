@@ -187,6 +187,19 @@ int  vds_supply_expect(vds_handle h, int tick, void *stream);
 int  vds_dispatch(vds_handle h, int tick, const int32_t *move_off, const int32_t *move_veh,
                   const int32_t *move_node, int total_moves, void *stream);
 
+/* Same primitive, fixed-stride layout: replica r applies move_cnt[r] moves stored at [r * stride, ...). */
+int  vds_dispatch_strided(vds_handle h, int tick, const int32_t *move_cnt, const int32_t *move_veh,
+                          const int32_t *move_node, int stride, void *stream);
+
+/* A DispatchFunction hook resident on the device (BASELINE config 4): after the match of `tick`, every idle
+ * vehicle moves with probability move_prob_q32 / 2^32 to a uniformly drawn node of a uniformly drawn
+ * neighbour cluster (Cluster.Neighbor CSR nb_off/nb_idx, Cluster.Nodes CSR cl_node_off/cl_nodes; device
+ * pointers).  Philox4x32-10 keyed by (seed, first_replica + r), counter (vehicle, tick).  Writes
+ * move_cnt[R], move_veh / move_node [R][stride] (stride >= vehicles) for vds_dispatch_strided. */
+int  vds_policy_random(vds_handle h, int tick, uint64_t seed, int64_t first_replica, uint32_t move_prob_q32,
+                       const int32_t *nb_off, const uint16_t *nb_idx, const int32_t *cl_node_off, const uint16_t *cl_nodes,
+                       int32_t *move_cnt, int32_t *move_veh, int32_t *move_node, int stride, void *stream);
+
 /* Hook-free ticks [tick0, tick0+nticks): update, match, supply_expect per tick
  * (the body of SimCity's loop, simulator.py:1048-1091, with empty hooks).
  * With prepared orders this is ONE launch of the replica-resident rollout

@@ -61,3 +61,29 @@ def replica_placement(valid_nodes, n_vehicles, seed, g):
     v = np.arange(n_vehicles, dtype=np.uint64)
     x0, _, _, _ = philox4x32_10(v, 2 << 16, g0, g1, k0, k1)
     return np.asarray(valid_nodes)[((x0 * np.uint64(len(valid_nodes))) >> np.uint64(32)).astype(np.int64)].astype(np.int32)
+
+
+def random_policy_moves(city, idle_vehicles, veh_cluster, tick, seed, g, prob):
+    """Host restatement of policy_random_kernel: (vehicle, node) moves of global replica g at `tick`, in vehicle
+    index order.  idle_vehicles: ascending vehicle indices that are idle after the match; veh_cluster[v]."""
+    k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+    g0, g1 = g & 0xFFFFFFFF, (g >> 32) & 0xFFFFFFFF
+    q32 = min(0xFFFFFFFF, int(prob * 4294967296.0))
+    v = np.asarray(idle_vehicles, dtype=np.uint64)
+    if len(v) == 0:
+        return np.zeros(0, np.int32), np.zeros(0, np.int32)
+    x0, x1, x2, _ = philox4x32_10(v, (3 << 16) | tick, g0, g1, k0, k1)
+    veh, node = [], []
+    for i in range(len(v)):
+        if int(x0[i]) >= q32:
+            continue
+        c = int(veh_cluster[int(v[i])])
+        nb = city.neighbors(c)
+        if len(nb) == 0:
+            continue
+        tc = int(nb[(int(x1[i]) * len(nb)) >> 32])
+        nodes = city.cluster_nodes[tc]
+        if len(nodes) == 0:
+            continue
+        veh.append(int(v[i])); node.append(int(nodes[(int(x2[i]) * len(nodes)) >> 32]))
+    return np.array(veh, np.int32), np.array(node, np.int32)

@@ -544,13 +544,14 @@ supply_kernel(DevParams P, int k)
 // The implied dispatch primitive (reference touch points
 // simulator.py:805-808, 889, 1018, 1117-1119).
 __global__ void __launch_bounds__(128)
-dispatch_kernel(DevParams P, int k, const int *move_off, const int *move_veh, const int *move_node)
+dispatch_kernel(DevParams P, int k, const int *move_off, const int *move_veh, const int *move_node, int stride)
 {
     __shared__ int s_n; __shared__ long long s_cost;
     const int r = blockIdx.x, tid = threadIdx.x;
     if (tid == 0) { s_n = 0; s_cost = 0; }
     __syncthreads();
-    const int m0 = move_off[r], m = move_off[r + 1] - m0;
+    // stride == 0: CSR over replicas (move_off[R+1]); stride > 0: move_off[r] = COUNT, lists at r * stride
+    const int m0 = stride ? r * stride : move_off[r], m = stride ? move_off[r] : move_off[r + 1] - m0;
     const size_t vb = (size_t)r * P.Vp;
     const int dseq = P.disp_seq[r];
     for (int i = tid; i < m; i += blockDim.x) {
@@ -712,6 +713,54 @@ __global__ void gen_placement_kernel(DevParams P, uint64_t seed, long long first
     const unsigned long long g = (unsigned long long)(first_replica + r);
     Philox x = philox4x32_10((uint32_t)v, 2u << 16, (uint32_t)g, (uint32_t)(g >> 32), (uint32_t)seed, (uint32_t)(seed >> 32));
     loc0[i] = valid_nodes[(uint32_t)(((uint64_t)x.c[0] * (uint64_t)n_valid) >> 32)];
+}
+
+// A DispatchFunction hook that lives on the device (BASELINE config 4, "random-policy Dispatch hook"): every
+// idle vehicle moves with probability p to a uniformly chosen node of a uniformly chosen neighbour cluster.
+// Philox4x32-10 keyed by (seed, GLOBAL replica id), counter (vehicle, tick): independent of the GPU split and
+// reproducible on the host (the tests restate it in NumPy).  Moves are emitted in vehicle-index order (the order the
+// dispatch primitive numbers them, i.e. the insertion order of the reference's VehiclesArrivetime dicts).
+__global__ void __launch_bounds__(UPD_THREADS)
+policy_random_kernel(DevParams P, int k, uint64_t seed, long long first_replica, uint32_t prob_q32,
+                     const int *nb_off, const uint16_t *nb_idx, const int *cl_node_off, const uint16_t *cl_nodes,
+                     int *move_cnt, int *move_veh, int *move_node, int stride)
+{
+    __shared__ int wsum[UPD_WARPS]; __shared__ int s_base;
+    const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const unsigned long long g = (unsigned long long)(first_replica + r);
+    const size_t vb = (size_t)r * P.Vp;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int v0 = 0; v0 < P.V; v0 += UPD_THREADS) {
+        const int v = v0 + tid;
+        int node = -1;
+        if (v < P.V && P.veh_arrive[vb + v] == IDLE16) {
+            const Philox x = philox4x32_10((uint32_t)v, (3u << 16) | (uint32_t)k, (uint32_t)g, (uint32_t)(g >> 32),
+                                           (uint32_t)seed, (uint32_t)(seed >> 32));
+            if (x.c[0] < prob_q32) {
+                const int c = P.veh_cluster[vb + v];
+                const int deg = nb_off[c + 1] - nb_off[c];
+                if (deg > 0) {
+                    const int tc = nb_idx[nb_off[c] + (int)(((uint64_t)x.c[1] * (uint64_t)deg) >> 32)];
+                    const int nn = cl_node_off[tc + 1] - cl_node_off[tc];
+                    if (nn > 0) node = cl_nodes[cl_node_off[tc] + (int)(((uint64_t)x.c[2] * (uint64_t)nn) >> 32)];
+                }
+            }
+        }
+        const unsigned bal = __ballot_sync(FULL, node >= 0);
+        if (lane == 0) wsum[w] = __popc(bal);
+        __syncthreads();
+        int off = s_base;
+        for (int ww = 0; ww < w; ww++) off += wsum[ww];
+        if (node >= 0) {
+            const int pos = off + __popc(bal & lanemask_lt());
+            move_veh[(size_t)r * stride + pos] = v; move_node[(size_t)r * stride + pos] = node;
+        }
+        __syncthreads();
+        if (tid == 0) { int t = 0; for (int ww = 0; ww < UPD_WARPS; ww++) t += wsum[ww]; s_base += t; }
+        __syncthreads();
+    }
+    if (tid == 0) move_cnt[r] = s_base;
 }
 
 // =========================================================== host-side C ABI
@@ -932,8 +981,33 @@ int vds_dispatch(vds_handle h, int tick, const int32_t *move_off, const int32_t 
     if (!move_off || (total_moves > 0 && (!move_veh || !move_node)))
         return fail(h, VDS_ERR_INVALID, "vds_dispatch: null pointer");
     if (total_moves <= 0) return VDS_OK;
-    dispatch_kernel<<<h->P.R, 128, 0, (cudaStream_t)stream>>>(h->P, tick, move_off, move_veh, move_node);
+    dispatch_kernel<<<h->P.R, 128, 0, (cudaStream_t)stream>>>(h->P, tick, move_off, move_veh, move_node, 0);
     CKL("dispatch_kernel");
+    return VDS_OK;
+}
+
+int vds_dispatch_strided(vds_handle h, int tick, const int32_t *move_cnt, const int32_t *move_veh,
+                         const int32_t *move_node, int stride, void *stream)
+{
+    int rc = ready(h, false); if (rc) return rc;
+    if (!move_cnt || !move_veh || !move_node || stride < 1)
+        return fail(h, VDS_ERR_INVALID, "vds_dispatch_strided: bad arguments");
+    dispatch_kernel<<<h->P.R, 128, 0, (cudaStream_t)stream>>>(h->P, tick, move_cnt, move_veh, move_node, stride);
+    CKL("dispatch_kernel");
+    return VDS_OK;
+}
+
+int vds_policy_random(vds_handle h, int tick, uint64_t seed, int64_t first_replica, uint32_t move_prob_q32,
+                      const int32_t *nb_off, const uint16_t *nb_idx, const int32_t *cl_node_off, const uint16_t *cl_nodes,
+                      int32_t *move_cnt, int32_t *move_veh, int32_t *move_node, int stride, void *stream)
+{
+    int rc = ready(h, false); if (rc) return rc;
+    if (!nb_off || !nb_idx || !cl_node_off || !cl_nodes || !move_cnt || !move_veh || !move_node || stride < h->P.V)
+        return fail(h, VDS_ERR_INVALID, "vds_policy_random: bad arguments (stride must be >= vehicles)");
+    policy_random_kernel<<<h->P.R, UPD_THREADS, 0, (cudaStream_t)stream>>>(h->P, tick, seed, first_replica, move_prob_q32,
+                                                                          nb_off, nb_idx, cl_node_off, cl_nodes,
+                                                                          move_cnt, move_veh, move_node, stride);
+    CKL("policy_random_kernel");
     return VDS_OK;
 }
 

@@ -298,6 +298,30 @@ class DispatchEngine:
             return
         self._ck(self.L.vds_dispatch(self.h, int(k), _ptr(mo), _ptr(mv), _ptr(mn), int(mv.numel()), self._stream()))
 
+    def policy_random_dispatch(self, k, seed=1234, first_replica=0, prob=0.05):
+        """Device-resident random DispatchFunction hook (BASELINE config 4) + the dispatch primitive for tick k:
+        every idle vehicle moves with probability `prob` to a random node of a random neighbour cluster."""
+        if getattr(self, "_pol", None) is None:
+            city, dev = self.city, self.device
+            nodes = city.cluster_nodes if city.cluster_nodes is not None else \
+                [np.nonzero(city.node2cluster == c)[0] for c in range(self.nC)]
+            noff = np.cumsum([0] + [len(n) for n in nodes]).astype(np.int32)
+            nflat = (np.concatenate([np.asarray(n, np.int64) for n in nodes]) if noff[-1] else np.zeros(1, np.int64)).astype(np.uint16)
+            t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+            self._pol = dict(nb_off=t(city.nb_off.astype(np.int32)), nb_idx=t(city.nb_idx.astype(np.uint16)),
+                             noff=t(noff), nflat=t(nflat),
+                             cnt=torch.zeros(self.R, dtype=torch.int32, device=dev),
+                             veh=torch.zeros((self.R, self.Vp), dtype=torch.int32, device=dev),
+                             node=torch.zeros((self.R, self.Vp), dtype=torch.int32, device=dev))
+        p = self._pol
+        q32 = min(0xFFFFFFFF, int(prob * 4294967296.0))
+        self._ck(self.L.vds_policy_random(self.h, int(k), C.c_uint64(seed), C.c_int64(first_replica), C.c_uint32(q32),
+                                          _ptr(p["nb_off"]), _ptr(p["nb_idx"]), _ptr(p["noff"]), _ptr(p["nflat"]),
+                                          _ptr(p["cnt"]), _ptr(p["veh"]), _ptr(p["node"]), self.Vp, self._stream()))
+        self._ck(self.L.vds_dispatch_strided(self.h, int(k), _ptr(p["cnt"]), _ptr(p["veh"]), _ptr(p["node"]),
+                                             self.Vp, self._stream()))
+        return p
+
     def rollout(self, tick0=0, nticks=None):
         """Hook-free ticks [tick0, tick0+nticks).  Depth-0 engines run ONE launch
         of the replica-resident kernel (see csrc/rollout.cuh)."""
