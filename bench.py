@@ -38,6 +38,9 @@ WORKLOADS = {
                     desc="1024 replicas x 192-grid x 2000 vehicles, synthetic Didi-rate orders, depth 0"),
     "config3": dict(replicas=4096, side=800, service=2800, ncs=True, vehicles=5000,
                     desc="4096 replicas x 192-grid x 5000 vehicles, neighbour-search depth 3"),
+    "config4": dict(replicas=1024, side=800, service=800, ncs=False, vehicles=2000, policy=0.05,
+                    desc="1024 replicas/GPU (8192 on 8 GPUs) x 192-grid x 2000 vehicles, device-resident random-policy "
+                         "Dispatch hook every tick, NCCL all-gather of returns"),
     "config5": dict(replicas=2048, side=400, service=400, ncs=False, vehicles=10000,
                     desc="2048 replicas/GPU x 768-grid x 10000 vehicles, depth 0"),
 }
@@ -52,6 +55,18 @@ def measured_peak_gbs():
         except Exception:
             pass
     return 6650.0, "fallback"
+
+
+def measured_traffic(workload, kernel):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/traffic.json);
+    None if no capture of this workload / kernel has been taken."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(workload)
+        if t and t["kernel"].split("<")[0] == kernel.split("<")[0]:
+            return {"bytes_per_launch": t["bytes_per_launch"], "source": t["capture"]}
+    except Exception:
+        pass
+    return None
 
 
 class ClockSampler:
@@ -244,9 +259,19 @@ def main():
     city, tables, eng, loc0 = build_workload(w, R, local_rank, shard.first_replica)
     T = eng.T
 
+    policy = w.get("policy")
+
+    def run_ticks():
+        if policy:      # hook every tick: one fused tick launch + policy kernel + dispatch primitive per time slot
+            for k in range(T):
+                eng.tick(k)
+                eng.policy_random_dispatch(k, seed=SEED, first_replica=shard.first_replica, prob=policy)
+        else:
+            eng.rollout(0, T)
+
     def episode():
         eng.reset(loc0)
-        eng.rollout(0, T)
+        run_ticks()
         st = eng.stats()
         return shard.all_gather_returns(st)
 
@@ -307,7 +332,7 @@ def main():
     def episode_e2e():
         d_loc.copy_(h_loc, non_blocking=True)
         eng.reset(d_loc)
-        eng.rollout(0, T)
+        run_ticks()
         out = shard.all_gather_returns(eng.stats())
         h_ret.copy_(out, non_blocking=True)
 
@@ -334,7 +359,21 @@ def main():
     # ---- per-kernel device times (CUDA events on the launch stream) and the roofline of the dominant kernel
     V, Cn = eng.V, eng.nC
     peak, peak_src = measured_peak_gbs()
-    if eng.fused:
+    if policy:
+        names = ("tick", "policy+dispatch")
+        evs = {n: [] for n in names}
+        eng.reset(loc0)
+        for k in range(T):
+            for n, fn in zip(names, (lambda: eng.tick(k), lambda: eng.policy_random_dispatch(
+                    k, seed=SEED, first_replica=shard.first_replica, prob=policy))):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); fn(); b.record()
+                evs[n].append((a, b))
+        torch.cuda.synchronize(dev)
+        kt = {n: float(sum(a.elapsed_time(b) for a, b in evs[n])) for n in names}      # ms per episode
+        dom, launches_per_episode = "tick", T
+        kname = "rollout_local_kernel<%d,local> (1-tick windows)" % eng.rollout_threads
+    elif eng.fused:
         # one launch of rollout_local_kernel == one whole episode of all R replicas
         evs = []
         for _ in range(max(3, args.steps)):
@@ -365,11 +404,15 @@ def main():
                "match": 12 * M + 8 * O + P + 4.0 * Cn * R * T,
                "supply": 4.0 * Cn * R * T}
     b_total = sum(bytes_k.values())
-    b_dom = b_total if eng.fused else bytes_k["match"]
+    D = st[:, 4].sum()
+    if policy:
+        bytes_k["policy+dispatch"] = 2.0 * V * R * T + 20.0 * D          # idle flags read + (move record + vehicle record) per move
+        b_total = sum(bytes_k.values())
+    b_dom = (b_total - bytes_k.get("policy+dispatch", 0.0)) if eng.fused else bytes_k["match"]
     ach = b_dom / (kt[dom] * 1e-3) / 1e9
     roof = {"bound": "hbm", "kernel": kname,
             "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak,
-            "traffic": None,
+            "traffic": measured_traffic(args.workload, kname),
             "avg_launch_us": 1e3 * kt[dom] / launches_per_episode,
             "algorithmic_bytes_per_launch": b_dom / launches_per_episode,
             "kernel_ms_per_episode": kt, "dominant_kernel": dom,
@@ -381,7 +424,7 @@ def main():
     # ---- CPU baseline + in-bench parity spot check (rank 0, N=1 only)
     cpu = None
     parity = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not policy:
         S = min(R, 4 * cores)
         v, wall, rounds, oracles = cpu_port_run(city, eng, loc0, tables, S, args.cpu_seconds, cores)
         cpu = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
