@@ -367,6 +367,7 @@ match_search_kernel(DevParams P, int k)
     int *ioff = sm + w * (3 * C + 2);       // [C+1]
     int *live = ioff + C + 1;               // [C]
     int *reach = live + C;                  // [C] idle vehicles anywhere in the cluster's search list
+    int *cmp = sm + MS_WARPS * (3 * C + 2) + w * 96;   // [3][32] compaction scratch of the flattened scan
     {
         const int *g_off = P.idle_off + (size_t)r * (C + 1);
         const int *g_lv = P.idle_live + (size_t)r * C;
@@ -408,58 +409,64 @@ match_search_kernel(DevParams P, int k)
             const int o_val = __shfl_sync(FULL, val, j);
             const int c = __shfl_sync(FULL, oc, j);
             const uint32_t rowoff = (o_pd & 0xFFFF) * (uint32_t)P.nodes;        // RoadCost(loc, pickup) = cost[pickup][loc]
-            // per-lane running best: (cost << 16 | search position) then idle key, lexicographic
+            // per-lane running best: (cost << 16 | search position) then idle key, lexicographic.  The idle slots
+            // of a cluster are kept COMPACT (a match swaps the last slot into the hole), so live[c] is its length.
             unsigned long long best = ~0ull; uint32_t ex = DEAD32; int idx = 0;
             auto offer = [&](uint2 t, uint32_t c2, uint32_t spos, int where) {
                 const unsigned long long v = ((unsigned long long)((c2 << 16) | spos) << 32) | t.y;
                 if (v < best) { best = v; ex = t.x; idx = where; }
             };
-            if (live[c] > 0) {
-                const int i0 = ioff[c], nn = ioff[c + 1] - i0;
-                for (int q0 = lane; q0 < nn; q0 += 64) {                          // 2 independent gathers in flight
+            const int own = live[c];
+            if (own > 0) {
+                const int i0 = ioff[c];
+                for (int q0 = lane; q0 < own; q0 += 64) {                         // 2 independent gathers in flight
                     uint2 t2[2]; uint32_t c2[2];
 #pragma unroll
-                    for (int u = 0; u < 2; u++) { t2[u] = make_uint2(DEAD32, DEAD32); if (q0 + 32 * u < nn) t2[u] = ent[i0 + q0 + 32 * u]; }
+                    for (int u = 0; u < 2; u++) if (q0 + 32 * u < own) t2[u] = ent[i0 + q0 + 32 * u];
 #pragma unroll
-                    for (int u = 0; u < 2; u++) if (t2[u].x != DEAD32) c2[u] = P.cost[rowoff + (t2[u].x >> 16)];
+                    for (int u = 0; u < 2; u++) if (q0 + 32 * u < own) c2[u] = P.cost[rowoff + (t2[u].x >> 16)];
 #pragma unroll
-                    for (int u = 0; u < 2; u++) if (t2[u].x != DEAD32) offer(t2[u], c2[u], 0, i0 + q0 + 32 * u);
+                    for (int u = 0; u < 2; u++) if (q0 + 32 * u < own) offer(t2[u], c2[u], 0, i0 + q0 + 32 * u);
                 }
-                my_lookups += lane == 0 ? live[c] : 0;
+                my_lookups += lane == 0 ? own : 0;
             } else if (P.ncs) {
-                // the idle slots of up to 32 clusters of the DFS pre-order list are FLATTENED over the lanes
-                // (prefix sum of list lengths + shuffle binary search), so all cost gathers of the order are in
-                // flight at once instead of cluster after cluster
+                // the idle slots of the non-empty clusters of the DFS pre-order list are FLATTENED over the lanes, so
+                // all cost gathers of the order are in flight at once: compact the non-empty clusters to the low
+                // lanes, prefix-sum their lengths; candidate j of a 32-wide window then belongs to cluster
+                //   #{clusters ending at or before the window start} + popc(end-boundary bits <= j)
                 const int s0 = P.soff[c], s1 = P.soff[c + 1];
                 for (int sb = s0 + 1; sb < s1; sb += 32) {                        // position 0 is c itself (empty)
                     const int cl = sb + lane < s1 ? (int)P.sidx[sb + lane] : -1;
                     const int lv = cl >= 0 ? live[cl] : 0;
-                    int i0 = 0, nn = 0;
-                    if (lv > 0) { i0 = ioff[cl]; nn = ioff[cl + 1] - i0; }
+                    const unsigned nonempty = __ballot_sync(FULL, lv > 0);
+                    if (!nonempty) continue;
                     my_lookups += lv;
+                    if (lv > 0) {
+                        const int rk = __popc(nonempty & lanemask_lt());
+                        cmp[rk] = lv; cmp[32 + rk] = ioff[cl]; cmp[64 + rk] = sb + lane - s0;
+                    }
+                    __syncwarp();
+                    const int K = __popc(nonempty);
+                    const int nn = lane < K ? cmp[lane] : 0, i0 = cmp[32 + lane], sp = cmp[64 + lane];
                     int incl = nn;
 #pragma unroll
                     for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += t; }
                     const int total = __shfl_sync(FULL, incl, 31);
-                    for (int j0 = 0; j0 < total; j0 += 64) {
-                        uint2 t2[2]; uint32_t c2[2], sp[2]; int wh[2];
-#pragma unroll
-                        for (int u = 0; u < 2; u++) {
-                            const int jj = j0 + 32 * u + lane;
-                            int pos = 0;                                           // smallest pos with incl[pos] > jj
-#pragma unroll
-                            for (int st = 16; st; st >>= 1) { const int v = __shfl_sync(FULL, incl, pos + st - 1); if (v <= jj) pos += st; }
-                            pos = min(pos, 31);
-                            const int excl = __shfl_sync(FULL, incl, pos) - __shfl_sync(FULL, nn, pos);
-                            const int base_i0 = __shfl_sync(FULL, i0, pos);
-                            t2[u] = make_uint2(DEAD32, DEAD32); sp[u] = (uint32_t)(sb + pos - s0); wh[u] = base_i0 + (jj - excl);
-                            if (jj < total) t2[u] = ent[wh[u]];
+                    for (int j0 = 0; j0 < total; j0 += 32) {
+                        const int before = __popc(__ballot_sync(FULL, lane < K && incl <= j0));
+                        const int eb = incl - j0;                                 // this cluster ends eb candidates into the window
+                        const unsigned W = __reduce_or_sync(FULL, (lane < K && eb >= 1 && eb <= 31) ? (1u << eb) : 0u);
+                        const int pos = min(before + __popc(W & ((2u << lane) - 2u)), 31);
+                        const int p_incl = __shfl_sync(FULL, incl, pos), p_nn = __shfl_sync(FULL, nn, pos);
+                        const int p_i0 = __shfl_sync(FULL, i0, pos), p_sp = __shfl_sync(FULL, sp, pos);
+                        const int jj = j0 + lane;
+                        if (jj < total) {
+                            const int wh = p_i0 + (jj - (p_incl - p_nn));
+                            const uint2 t = ent[wh];
+                            offer(t, P.cost[rowoff + (t.x >> 16)], (uint32_t)p_sp, wh);
                         }
-#pragma unroll
-                        for (int u = 0; u < 2; u++) if (t2[u].x != DEAD32) c2[u] = P.cost[rowoff + (t2[u].x >> 16)];
-#pragma unroll
-                        for (int u = 0; u < 2; u++) if (t2[u].x != DEAD32) offer(t2[u], c2[u], sp[u], wh[u]);
                     }
+                    __syncwarp();
                 }
             }
             const uint32_t hi = (uint32_t)(best >> 32), lo = (uint32_t)best;
@@ -480,14 +487,15 @@ match_search_kernel(DevParams P, int k)
             const int src = spos ? (int)P.sidx[P.soff[c] + spos] : c;
             if (lane == win) {
                 const int v = ex & 0xFFFF;
-                int d = ((int)mn + o_val + P.period - 1) / P.period; if (d < 1) d = 1;
+                int d = (int)((((uint32_t)mn + (uint32_t)o_val + (uint32_t)P.period - 1u) * P.period_magic) >> 20); if (d < 1) d = 1;
                 const int dnode = o_pd >> 16;
                 P.veh_arrive[vb + v] = (uint16_t)((k + d) | 0x8000);
                 P.veh_dest[vb + v] = (uint16_t)dnode;
                 P.veh_cluster[vb + v] = P.n2c[dnode];
                 P.veh_key[vb + v] = ((uint32_t)k << 21) | (uint32_t)(base + j);
                 res[base + j] = (uint32_t)v | (mn << 16) | ((uint32_t)d << 24);
-                ent[idx].x = DEAD32;
+                const int last = ioff[src] + live[src] - 1;                         // IdleVehicles.remove (:963): keep the slots compact
+                if (idx != last) ent[idx] = ent[last];
                 live[src] -= 1;
             }
             for (int q = P.roff[src] + lane; q < P.roff[src + 1]; q += 32) reach[P.ridx[q]] -= 1;
@@ -959,7 +967,7 @@ int vds_match(vds_handle h, int tick, void *stream)
         match_local_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(P, tick);
         CKL("match_local_kernel");
     } else {
-        const int smem = (int)sizeof(int) * MS_WARPS * (3 * P.C + 2);
+        const int smem = (int)sizeof(int) * MS_WARPS * (3 * P.C + 2 + 96);
         match_search_kernel<<<(P.R + MS_WARPS - 1) / MS_WARPS, MS_WARPS * 32, smem, (cudaStream_t)stream>>>(P, tick);
         CKL("match_search_kernel");
     }
