@@ -11,6 +11,12 @@ from tests.helpers import (SMALL_CASES, golden_city, load_golden, lockstep, make
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _fused_search(monkeypatch):
+    """the speculative replica-resident search variant is opt-in (read by vds_create); these tests cover it"""
+    monkeypatch.setenv("VDS_FUSED_SEARCH", "1")
+
+
 def _city(side=800, service=800, ncs=False, n_nodes=700):
     from vehicles_dispatch_simulator_b200.synthetic import synthetic_grid_city
     return synthetic_grid_city(side_m=side, service_m=service, neighbor_can_server=ncs, n_nodes=n_nodes)

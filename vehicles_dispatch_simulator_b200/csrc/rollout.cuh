@@ -51,8 +51,8 @@ __host__ __device__ inline RollLayout roll_layout(int Vp, int C)
     L.wtot = o;   o += 4 * 40;
     L.acc = o;    o += 8 * 8;
     L.ooff = o;   o += 2 * (Cp + 8);
-    L.wl_pd = o;  o += 4 * Cp;
     L.wl_cnt = o; o += 16;
+    L.wl_pd = o;  o += 4 * Cp;
     L.wl = o;     o += 2 * Cp;
     L.wl_ix = o;  o += 2 * Cp;
     if (o - L.wl_pd < 6 * 128) o = L.wl_pd + 6 * 128;        // search variant: 6 x u32[32] speculation records alias this region
@@ -329,35 +329,67 @@ rollout_local_kernel(DevParams P, int k0, int nticks)
             for (int i = tid; i < Cp; i += THREADS) icnt[i] = 0;
             __syncthreads();
         }
-        for (int g = tid; g < ngroups; g += THREADS) {
-            U16x8 a; a.v = reinterpret_cast<uint4 *>(arrive)[g];
-            unsigned arriving = 0, idle = 0;
+        if (first) {
+            for (int g = tid; g < ngroups; g += THREADS) {
+                U16x8 a; a.v = reinterpret_cast<uint4 *>(arrive)[g];
+                unsigned arriving = 0, idle = 0;
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const unsigned t = a.h[j];
-                if (t == IDLE16) idle |= 1u << j;
-                else if ((int)(t & 0x7FFF) <= k) arriving |= 1u << j;
-            }
-            if (arriving) {
-#pragma unroll
-                for (int j = 0; j < 8; j++) if (arriving >> j & 1) {
-                    const int v = g * 8 + j;
-                    const uint32_t kk = key[v];
-                    const int at = a.h[j] & 0x7FFF;
-                    const int dt = at - (int)(kk >> 21);                  // ticks en route (1..63)
-                    key[v] = ((uint32_t)at << 21) | ((uint32_t)(63 - dt) << 15) | (kk & 0x7FFF);
-                    a.h[j] = IDLE16;                                      // objects.py:84-89 (node already holds DeliveryPoint)
-                    a_arrive++;
-                    if (!first) atomicAdd(&icnt[clus[v]], 1u);
+                for (int j = 0; j < 8; j++) {
+                    const unsigned t = a.h[j];
+                    if (t == IDLE16) idle |= 1u << j;
+                    else if ((int)(t & 0x7FFF) <= k) arriving |= 1u << j;
                 }
-                reinterpret_cast<uint4 *>(arrive)[g] = a.v;
-                idle |= arriving;
-            }
-            if (first && idle) {
-                U16x8 c; c.v = reinterpret_cast<uint4 *>(clus)[g];
+                if (arriving) {
 #pragma unroll
-                for (int j = 0; j < 8; j++) if (idle >> j & 1) atomicAdd(&icnt[c.h[j]], 1u);
+                    for (int j = 0; j < 8; j++) if (arriving >> j & 1) {
+                        const int v = g * 8 + j;
+                        const uint32_t kk = key[v];
+                        const int at = a.h[j] & 0x7FFF;
+                        const int dt = at - (int)(kk >> 21);                  // ticks en route (1..63)
+                        key[v] = ((uint32_t)at << 21) | ((uint32_t)(63 - dt) << 15) | (kk & 0x7FFF);
+                        a.h[j] = IDLE16;                                      // objects.py:84-89 (node already holds DeliveryPoint)
+                        a_arrive++;
+                    }
+                    reinterpret_cast<uint4 *>(arrive)[g] = a.v;
+                    idle |= arriving;
+                }
+                if (idle) {
+                    U16x8 c; c.v = reinterpret_cast<uint4 *>(clus)[g];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) if (idle >> j & 1) atomicAdd(&icnt[c.h[j]], 1u);
+                }
             }
+        } else {
+            // later ticks: only ARRIVALS change the counts.  The packed scan just queues the arriving vehicles
+            // (the idle-slot pool is free until phase 4 and serves as the queue); they are then handled densely,
+            // one thread each, instead of through eight predicated per-slot blocks per thread.
+            if (tid == 0) wl_cnt[3] = 0;
+            __syncthreads();
+            for (int g = tid; g < ngroups; g += THREADS) {
+                U16x8 a; a.v = reinterpret_cast<uint4 *>(arrive)[g];
+                unsigned arriving = 0;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const unsigned t = a.h[j];
+                    if (t != IDLE16 && (int)(t & 0x7FFF) <= k) arriving |= 1u << j;
+                }
+                while (arriving) {
+                    const int j = __ffs(arriving) - 1; arriving &= arriving - 1;
+                    ent[atomicAdd(&wl_cnt[3], 1u)] = (uint32_t)(g * 8 + j);
+                }
+            }
+            __syncthreads();
+            const int n_arr = (int)wl_cnt[3];
+            for (int i = tid; i < n_arr; i += THREADS) {
+                const int v = (int)ent[i];
+                const uint32_t kk = key[v];
+                const int at = arrive[v] & 0x7FFF;
+                const int dt = at - (int)(kk >> 21);                          // ticks en route (1..63)
+                key[v] = ((uint32_t)at << 21) | ((uint32_t)(63 - dt) << 15) | (kk & 0x7FFF);
+                arrive[v] = IDLE16;                                           // objects.py:84-89 (node already holds DeliveryPoint)
+                atomicAdd(&icnt[clus[v]], 1u);
+            }
+            if (tid == 0) a_arrive += (unsigned)n_arr;
         }
 #pragma unroll
         for (int i = 0; i < OPT; i++) { const int c = tid + i * THREADS; if (c <= C) ooff[c] = my_off[i]; }
@@ -394,7 +426,13 @@ rollout_local_kernel(DevParams P, int k0, int nticks)
         //      matches overwrite their slot.  Coalesced stores, original order.
         {
             uint32_t *p = res_base + tb;
-            for (int i = tid; i < n_tick; i += THREADS) p[i] = 0x0000FFFFu;
+            const int head = min(n_tick, (int)((16u - ((uint32_t)(uintptr_t)p & 15u)) & 15u) >> 2);   // up to the 16-byte boundary
+            const int n4 = (n_tick - head) >> 2;
+            if (tid < head) p[tid] = 0x0000FFFFu;
+            uint4 *p4 = reinterpret_cast<uint4 *>(p + head);
+            for (int i = tid; i < n4; i += THREADS) p4[i] = make_uint4(0x0000FFFFu, 0x0000FFFFu, 0x0000FFFFu, 0x0000FFFFu);
+            const int tail0 = head + 4 * n4;
+            if (tail0 + tid < n_tick) p[tail0 + tid] = 0x0000FFFFu;
             if (tid < 4) wl_cnt[tid] = 0;
         }
         __syncthreads();
