@@ -118,6 +118,20 @@ def test_fused_search_equals_per_phase_state(cuda_device):
     assert bool((sa[:, keep] == sb[:, keep]).all())
 
 
+@pytest.mark.parametrize("side,ncs,service", [(400, False, 400), (400, True, 1000), (1500, False, 1500)])
+def test_fused_rollout_other_grids(cuda_device, side, ncs, service):
+    """768-cell grid (C > 256, several classification rounds per thread, empty cells) and a coarse 24-cell grid
+    (C not a multiple of 4, idle lists of hundreds of vehicles)"""
+    from vehicles_dispatch_simulator_b200.synthetic import synthetic_grid_city
+    rng = np.random.default_rng(side)
+    city = synthetic_grid_city(side_m=side, service_m=service, neighbor_can_server=ncs, n_nodes=900)
+    V = 1200
+    minute, pick, drop = random_orders(city, 6000, rng)
+    loc0 = rng.choice(city.valid_nodes(), (2, V)).astype(np.int32)
+    e = _engine(city, V, minute, pick, drop, R=2, trace=True)
+    rollout_vs_oracle(e, [make_oracle(city, V, minute, pick, drop) for _ in range(2)], loc0, [3, 1, e.T - 4])
+
+
 def test_fused_rollout_single_hot_cluster(cuda_device):
     """every vehicle and every pickup in ONE cluster: idle list of V entries, long sequential chain, ties."""
     rng = np.random.default_rng(2)
