@@ -29,7 +29,7 @@
  *                      seq = vehicle index).  Ascending key == position in the
  *                     reference's Cluster.IdleVehicles list.
  *   order_pd    u32 : pickup_node | delivery_node << 16
- *   order_res   u32 : 0xFFFFFFFF = not processed (ArriveInfo None);
+ *   order_res   u32 : 0xFFFFFFFF = not processed (ArriveInfo None; see vds_clear_results);
  *                     else vehicle | wait_minutes<<16 | arrive_delta_ticks<<24
  *                     with vehicle 0xFFFF = "Reject".
  */
@@ -167,6 +167,12 @@ int  vds_prepare_orders(vds_handle h, const int32_t *n_orders, void *stream);
 /* Reset + InitVehiclesIntoCluster with the caller's placement
  * (simulator.py:214-258).  veh_loc0: [R][V] uint16 node per vehicle. */
 int  vds_reset(vds_handle h, const uint16_t *veh_loc0, void *stream);
+
+/* order_res := 0xFFFFFFFF ("not processed").  vds_reset does NOT do this: the result range of a tick is
+ * completely rewritten whenever that tick is matched, so after a reset only the ranges of ticks that have
+ * been matched since are meaningful (the caller knows which ticks it ran); callers that want the sentinel
+ * for the others -- e.g. the stream's last order, which is never processed (Q8) -- call this once. */
+int  vds_clear_results(vds_handle h, void *stream);
 
 /* UpdateFunction (simulator.py:1006-1024) for tick k: arrivals -> idle lists;
  * also rebuilds the per-cluster idle slots, PerMatchIdleVehicles and this

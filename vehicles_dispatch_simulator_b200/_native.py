@@ -57,7 +57,7 @@ class State(C.Structure):
 # every symbol include/vds.h declares (tests check the export list against this)
 EXPORTS = ("vds_abi_version", "vds_padded_vehicles", "vds_create", "vds_destroy", "vds_last_error",
            "vds_bind_static", "vds_bind_orders", "vds_bind_state", "vds_compute_order_values",
-           "vds_prepare_orders", "vds_reset", "vds_update", "vds_match", "vds_supply_expect", "vds_dispatch", "vds_dispatch_strided", "vds_policy_random", "vds_rollout", "vds_tick", "vds_rollout_is_fused", "vds_rollout_threads",
+           "vds_prepare_orders", "vds_reset", "vds_clear_results", "vds_update", "vds_match", "vds_supply_expect", "vds_dispatch", "vds_dispatch_strided", "vds_policy_random", "vds_rollout", "vds_tick", "vds_rollout_is_fused", "vds_rollout_threads",
            "vds_stats", "vds_sync", "vds_launch_count", "vds_generate_orders", "vds_generate_placement")
 
 
@@ -98,6 +98,7 @@ def lib():
         "vds_compute_order_values": (C.c_int, [vp, vp, vp, vp, vp, vp]),
         "vds_prepare_orders": (C.c_int, [vp, vp, vp]),
         "vds_reset": (C.c_int, [vp, vp, vp]),
+        "vds_clear_results": (C.c_int, [vp, vp]),
         "vds_update": (C.c_int, [vp, i32, vp]),
         "vds_match": (C.c_int, [vp, i32, vp]),
         "vds_supply_expect": (C.c_int, [vp, i32, vp]),

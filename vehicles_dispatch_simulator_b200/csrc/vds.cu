@@ -937,12 +937,20 @@ int vds_reset(vds_handle h, const uint16_t *veh_loc0, void *stream)
     if (!veh_loc0) return fail(h, VDS_ERR_INVALID, "vds_reset: null placement");
     cudaStream_t st = (cudaStream_t)stream;
     const DevParams &P = h->P;
-    CK(cudaMemsetAsync(P.order_res, 0xFF, sizeof(uint32_t) * (size_t)P.R * P.Nmax, st));
+    // order_res is NOT cleared here (it is R x N_max words, as much HBM traffic as a whole episode's rollout):
+    // a tick's result range is fully rewritten when that tick is matched; see vds_clear_results.
     long long tot = (long long)P.R * P.Vp;
     long long t2 = (long long)P.R * (P.C > VDS_NUM_STATS ? P.C : VDS_NUM_STATS);
     if (t2 > tot) tot = t2;
     reset_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(P, veh_loc0);
     CKL("reset_kernel");
+    return VDS_OK;
+}
+
+int vds_clear_results(vds_handle h, void *stream)
+{
+    int rc = ready(h, false); if (rc) return rc;
+    CK(cudaMemsetAsync(h->P.order_res, 0xFF, sizeof(uint32_t) * (size_t)h->P.R * h->P.Nmax, (cudaStream_t)stream));
     return VDS_OK;
 }
 

@@ -275,6 +275,7 @@ class DispatchEngine:
         t = t.contiguous()
         assert t.shape == (self.R, self.V)
         self._loc0 = t
+        self._done_upto = 0          # ticks [0, _done_upto) have been matched since this reset
         with torch.cuda.device(self.device):
             self._ck(self.L.vds_reset(self.h, _ptr(t), self._stream()))
 
@@ -283,6 +284,7 @@ class DispatchEngine:
 
     def match(self, k):
         self._ck(self.L.vds_match(self.h, int(k), self._stream()))
+        self._done_upto = max(self._done_upto, int(k) + 1)
 
     def supply_expect(self, k):
         self._ck(self.L.vds_supply_expect(self.h, int(k), self._stream()))
@@ -327,10 +329,16 @@ class DispatchEngine:
         of the replica-resident kernel (see csrc/rollout.cuh)."""
         nticks = self.T - tick0 if nticks is None else nticks
         self._ck(self.L.vds_rollout(self.h, int(tick0), int(nticks), self._stream()))
+        self._done_upto = max(self._done_upto, int(tick0) + int(nticks))
 
     def tick(self, k):
         """One fused tick (update + match + supply_expect)."""
         self._ck(self.L.vds_tick(self.h, int(k), self._stream()))
+        self._done_upto = max(self._done_upto, int(k) + 1)
+
+    def clear_results(self):
+        """order_res := "not processed" everywhere (reset does not do it, see include/vds.h)."""
+        self._ck(self.L.vds_clear_results(self.h, self._stream()))
 
     @property
     def fused(self):
@@ -355,6 +363,9 @@ class DispatchEngine:
         ro = 0 if self.OR == 1 else replica
         n = int(self.n_orders_total[ro].item())
         res = self.tensors["order_res"][replica, :n].cpu().numpy().astype(np.uint32)
+        # only ticks matched since the last reset carry results (vds_reset does not clear order_res)
+        done = int(self.tick_off[ro, min(getattr(self, "_done_upto", self.T), self.T)].item())
+        res[done:] = UNPROCESSED
         veh = (res & 0xFFFF).astype(np.int32)
         wait = ((res >> 16) & 0xFF).astype(np.int32)
         delta = (res >> 24).astype(np.int32)
