@@ -81,10 +81,11 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise VdsError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`. "
+    path = os.environ.get("VDS_LIB_PATH", LIB_PATH)       # developer knob: A/B-test a kernel variant built elsewhere
+    if not os.path.exists(path):
+        raise VdsError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`. "
                        "The dispatch hot path is CUDA-only; there is no CPU fallback.")
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(path)
     vp, i32, i64, u64 = C.c_void_p, C.c_int, C.c_int64, C.c_uint64
     sig = {
         "vds_abi_version": (C.c_int, []),

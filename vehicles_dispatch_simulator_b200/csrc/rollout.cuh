@@ -32,6 +32,19 @@
 
 #define ROLL_DEAD 0xFFFFFFFFu
 
+// Developer instrumentation (-DROLL_PROF): per-warp clock64 deltas per phase, summed into g_roll_prof
+// (read with vds_debug_prof; profiles/phase_profile.py).  Compiled out of the product build.
+#ifdef ROLL_PROF
+__device__ unsigned long long g_roll_prof[16];
+#define RPROF_DECL unsigned long long rp_[16] = {0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0}; long long rp_t = clock64();
+#define RPROF(i) { const long long t_ = clock64(); rp_[i] += (unsigned long long)(t_ - rp_t); rp_t = t_; }
+#define RPROF_END if (lane == 0) { for (int i_ = 0; i_ < 16; i_++) atomicAdd(&g_roll_prof[i_], rp_[i_]); }
+#else
+#define RPROF_DECL
+#define RPROF(i)
+#define RPROF_END
+#endif
+
 struct RollLayout {
     int key, ent, arrive, node, clus, icnt, ioff, wtot, ooff, acc, wl, wl_ix, wl_pd, wl_cnt, total;
 };
@@ -310,6 +323,7 @@ rollout_local_kernel(DevParams P, int k0, int nticks)
     const uint32_t thr32 = P.threshold > 0xFFFFFFF0LL ? 0xFFFFFFF0u : (P.threshold < 0 ? 0u : (uint32_t)P.threshold);
     long long a_orders = 0, a_tickval = 0;          // thread 0 only
     __syncthreads();
+    RPROF_DECL
 
     for (int k = k0; k < k0 + nticks; k++) {
         const bool emit = (k == k0 + nticks - 1) || P.trace != nullptr;
@@ -364,7 +378,9 @@ rollout_local_kernel(DevParams P, int k0, int nticks)
             // (the idle-slot pool is free until phase 4 and serves as the queue); they are then handled densely,
             // one thread each, instead of through eight predicated per-slot blocks per thread.
             if (tid == 0) wl_cnt[3] = 0;
+            RPROF(11)
             __syncthreads();
+            RPROF(12)
             for (int g = tid; g < ngroups; g += THREADS) {
                 U16x8 a; a.v = reinterpret_cast<uint4 *>(arrive)[g];
                 unsigned arriving = 0;
@@ -378,7 +394,9 @@ rollout_local_kernel(DevParams P, int k0, int nticks)
                     ent[atomicAdd(&wl_cnt[3], 1u)] = (uint32_t)(g * 8 + j);
                 }
             }
+            RPROF(13)
             __syncthreads();
+            RPROF(14)
             const int n_arr = (int)wl_cnt[3];
             for (int i = tid; i < n_arr; i += THREADS) {
                 const int v = (int)ent[i];
@@ -390,11 +408,14 @@ rollout_local_kernel(DevParams P, int k0, int nticks)
                 atomicAdd(&icnt[clus[v]], 1u);
             }
             if (tid == 0) a_arrive += (unsigned)n_arr;
+            RPROF(15)
         }
 #pragma unroll
         for (int i = 0; i < OPT; i++) { const int c = tid + i * THREADS; if (c <= C) ooff[c] = my_off[i]; }
         for (int c = tid + OPT * THREADS; c <= C; c += THREADS) ooff[c] = coff[c];
+        RPROF(0)
         __syncthreads();
+        RPROF(1)
 
         // ---- phase 3: idle offsets; PerMatchIdleVehicles
         block_scan_u32<THREADS>(icnt, ioff, C, wtot);
@@ -407,6 +428,7 @@ rollout_local_kernel(DevParams P, int k0, int nticks)
             }
         }
 
+        RPROF(2)
         // ---- phase 4: per-cluster idle slots {vehicle | node << 16}; ioff[c] ends as END offset of c
         for (int g = tid; g < ngroups; g += THREADS) {
             U16x8 a; a.v = reinterpret_cast<uint4 *>(arrive)[g];
@@ -435,7 +457,9 @@ rollout_local_kernel(DevParams P, int k0, int nticks)
             if (tail0 + tid < n_tick) p[tail0 + tid] = 0x0000FFFFu;
             if (tid < 4) wl_cnt[tid] = 0;
         }
+        RPROF(3)
         __syncthreads();
+        RPROF(4)
 
         // ---- phase 6: match.  cluster c = (slot * NW + w), slot = round * 32 + lane
         unsigned t_match = 0, t_val = 0, t_wait = 0, t_look = 0;      // per-THREAD, reduced at window end
@@ -461,7 +485,9 @@ rollout_local_kernel(DevParams P, int k0, int nticks)
                 wl[slot] = (uint16_t)c_l; wl_pd[slot] = pd0_l; wl_ix[slot] = (uint16_t)idx0_l;
             }
         }
+        RPROF(5)
         __syncthreads();
+        RPROF(6)
         {
             const int n_lp = (int)wl_cnt[1];
             for (int i = tid; i < n_lp; i += THREADS) {                  // dense: no idle lanes between small clusters
@@ -473,6 +499,7 @@ rollout_local_kernel(DevParams P, int k0, int nticks)
                 t_match += st.x; t_wait += st.y; t_val += st.z; t_look += st.w;
             }
         }
+        RPROF(7)
         // -- 6b: warps pop clusters off the work list: lanes over the cluster's idle slots
         {
             const int n_work = (int)wl_cnt[0];
@@ -628,7 +655,9 @@ rollout_local_kernel(DevParams P, int k0, int nticks)
         }
         a_match += t_match; a_val += t_val; a_wait += t_wait; a_look += t_look;
         if (tid == 0) { a_orders += n_tick; a_tickval += P.tick_value[(size_t)ro * P.T + k]; }
+        RPROF(8)
         __syncthreads();
+        RPROF(9)
 
         // ---- phase 7: snapshots + SupplyExpectFunction (only where observable)
         if (emit) {
@@ -662,6 +691,8 @@ rollout_local_kernel(DevParams P, int k0, int nticks)
         }
     }
 
+    RPROF(10)
+    RPROF_END
     // ---- window end: shared memory -> HBM vehicle table, counters
     {
         uint4 *g_arr = reinterpret_cast<uint4 *>(P.veh_arrive + vb);

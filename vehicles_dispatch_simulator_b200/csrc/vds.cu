@@ -1084,6 +1084,15 @@ int vds_sync(vds_handle h, void *stream)
 }
 
 int64_t vds_launch_count(vds_handle h) { return h ? h->launches : 0; }
+#ifdef ROLL_PROF
+int vds_debug_prof(unsigned long long *out16, int clear)     /* developer builds only (-DROLL_PROF) */
+{
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out16, g_roll_prof, sizeof(unsigned long long) * 16);
+    if (clear) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_roll_prof, z, sizeof(z)); }
+    return 0;
+}
+#endif
 
 int vds_generate_orders(vds_handle h, uint64_t seed, int64_t first_replica,
                         const uint32_t *slot_cdf, const int32_t *slot_base, int n_slots, int cdf_len,
