@@ -56,6 +56,7 @@ struct vds_handle_s {
     DevParams P;
     bool have_static, have_orders, have_state, have_sorted, prepared, fused_search;
     int roll_threads, roll_smem;
+    int n_sidx, n_ridx;                      // search-list sizes: decide the shared-memory staging of match_search_kernel
     char err[512];
     int64_t launches;
     int sm_count;
@@ -355,19 +356,34 @@ match_local_kernel(DevParams P, int k)
 // precomputed DFS pre-order list; a match can remove a vehicle from ANY
 // cluster, so orders of one replica are processed strictly in index order by
 // one warp; replicas are the parallel dimension.
-#define MS_WARPS 4
+// The search lists and their inverses (read on every order's dependent chain) are staged in shared memory
+// once per CTA when they fit (`staged`; sizes from vds_bind_static).
+#define MS_WARPS 8
 __global__ void __launch_bounds__(MS_WARPS * 32)
-match_search_kernel(DevParams P, int k)
+match_search_kernel(DevParams P, int k, int staged, int n_sidx, int n_ridx)
 {
     extern __shared__ int sm[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int C = P.C;
+    const int *soff = P.soff, *roff = P.roff; const uint16_t *sidx = P.sidx, *ridx = P.ridx;
+    int tab_ints = 0;
+    if (staged) {
+        int *soff_s = sm, *roff_s = sm + (C + 1);
+        uint16_t *sidx_s = reinterpret_cast<uint16_t *>(sm + 2 * (C + 1));
+        uint16_t *ridx_s = sidx_s + ((n_sidx + 1) & ~1);
+        tab_ints = 2 * (C + 1) + ((n_sidx + 1) >> 1) + ((n_ridx + 1) >> 1);
+        for (int i = threadIdx.x; i <= C; i += blockDim.x) { soff_s[i] = P.soff[i]; roff_s[i] = P.roff[i]; }
+        for (int i = threadIdx.x; i < n_sidx; i += blockDim.x) sidx_s[i] = P.sidx[i];
+        for (int i = threadIdx.x; i < n_ridx; i += blockDim.x) ridx_s[i] = P.ridx[i];
+        __syncthreads();
+        soff = soff_s; roff = roff_s; sidx = sidx_s; ridx = ridx_s;
+    }
     const int r = blockIdx.x * MS_WARPS + w;
     if (r >= P.R) return;
-    const int C = P.C;
-    int *ioff = sm + w * (3 * C + 2);       // [C+1]
+    int *ioff = sm + tab_ints + w * (3 * C + 2);       // [C+1]
     int *live = ioff + C + 1;               // [C]
     int *reach = live + C;                  // [C] idle vehicles anywhere in the cluster's search list
-    int *cmp = sm + MS_WARPS * (3 * C + 2) + w * 96;   // [3][32] compaction scratch of the flattened scan
+    int *cmp = sm + tab_ints + MS_WARPS * (3 * C + 2) + w * 96;   // [3][32] compaction scratch of the flattened scan
     {
         const int *g_off = P.idle_off + (size_t)r * (C + 1);
         const int *g_lv = P.idle_live + (size_t)r * C;
@@ -377,7 +393,7 @@ match_search_kernel(DevParams P, int k)
     __syncwarp();
     for (int i = lane; i < C; i += 32) {
         int s = 0;
-        if (P.ncs) for (int q = P.soff[i]; q < P.soff[i + 1]; q++) s += live[P.sidx[q]];
+        if (P.ncs) for (int q = soff[i]; q < soff[i + 1]; q++) s += live[sidx[q]];
         else s = live[i];
         reach[i] = s;
     }
@@ -434,9 +450,9 @@ match_search_kernel(DevParams P, int k)
                 // all cost gathers of the order are in flight at once: compact the non-empty clusters to the low
                 // lanes, prefix-sum their lengths; candidate j of a 32-wide window then belongs to cluster
                 //   #{clusters ending at or before the window start} + popc(end-boundary bits <= j)
-                const int s0 = P.soff[c], s1 = P.soff[c + 1];
+                const int s0 = soff[c], s1 = soff[c + 1];
                 for (int sb = s0 + 1; sb < s1; sb += 32) {                        // position 0 is c itself (empty)
-                    const int cl = sb + lane < s1 ? (int)P.sidx[sb + lane] : -1;
+                    const int cl = sb + lane < s1 ? (int)sidx[sb + lane] : -1;
                     const int lv = cl >= 0 ? live[cl] : 0;
                     const unsigned nonempty = __ballot_sync(FULL, lv > 0);
                     if (!nonempty) continue;
@@ -484,7 +500,7 @@ match_search_kernel(DevParams P, int k)
             }
             const int win = __ffs(tied) - 1;
             const uint32_t spos = hmin & 0xFFFF;
-            const int src = spos ? (int)P.sidx[P.soff[c] + spos] : c;
+            const int src = spos ? (int)sidx[soff[c] + spos] : c;
             if (lane == win) {
                 const int v = ex & 0xFFFF;
                 int d = (int)((((uint32_t)mn + (uint32_t)o_val + (uint32_t)P.period - 1u) * P.period_magic) >> 20); if (d < 1) d = 1;
@@ -498,7 +514,7 @@ match_search_kernel(DevParams P, int k)
                 if (idx != last) ent[idx] = ent[last];
                 live[src] -= 1;
             }
-            for (int q = P.roff[src] + lane; q < P.roff[src + 1]; q += 32) reach[P.ridx[q]] -= 1;
+            for (int q = roff[src] + lane; q < roff[src + 1]; q += 32) reach[ridx[q]] -= 1;
             __syncwarp();
             matches++; wait_sum += mn;
         }
@@ -832,6 +848,7 @@ int vds_create(const vds_config *cfg, vds_handle *out)
     const int prep_smem = (int)sizeof(int) * (2 * Cp + 4 + 16 + PREP_WARPS * Cp);
     CK(cudaFuncSetAttribute(prepare_orders_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, prep_smem));
     { const char *e = getenv("VDS_FUSED_SEARCH"); h->fused_search = e && e[0] == '1'; }
+    CK(cudaFuncSetAttribute(match_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     // replica-resident rollout kernel: pick the CTA width from how many replicas fit one SM
     h->roll_smem = roll_layout(P.Vp, P.C).total;
     h->roll_threads = 0;
@@ -859,6 +876,13 @@ int vds_bind_static(vds_handle h, const vds_static *s)
     h->P.roff = s->reach_off; h->P.ridx = s->reach_idx;
     if (!local_mode(h) && (!s->reach_off || !s->reach_idx))
         return fail(h, VDS_ERR_INVALID, "vds_bind_static: reach_off / reach_idx are required with neighbour search");
+    h->n_sidx = h->n_ridx = -1;
+    if (!local_mode(h)) {                          // list sizes decide whether the tables are staged in shared memory
+        int a = 0, b = 0;
+        CK(cudaMemcpy(&a, s->search_off + h->P.C, sizeof(int), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(&b, s->reach_off + h->P.C, sizeof(int), cudaMemcpyDeviceToHost));
+        h->n_sidx = a; h->n_ridx = b;
+    }
     h->have_static = true; return VDS_OK;
 }
 int vds_bind_orders(vds_handle h, const vds_orders *o)
@@ -975,8 +999,12 @@ int vds_match(vds_handle h, int tick, void *stream)
         match_local_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(P, tick);
         CKL("match_local_kernel");
     } else {
-        const int smem = (int)sizeof(int) * MS_WARPS * (3 * P.C + 2 + 96);
-        match_search_kernel<<<(P.R + MS_WARPS - 1) / MS_WARPS, MS_WARPS * 32, smem, (cudaStream_t)stream>>>(P, tick);
+        const int per_cta = MS_WARPS * (3 * P.C + 2 + 96);
+        const int tab = 2 * (P.C + 1) + ((h->n_sidx + 1) >> 1) + ((h->n_ridx + 1) >> 1);
+        const int staged = h->n_sidx >= 0 && (size_t)(tab + per_cta) * sizeof(int) <= 64 * 1024;
+        const int smem = (int)sizeof(int) * ((staged ? tab : 0) + per_cta);
+        match_search_kernel<<<(P.R + MS_WARPS - 1) / MS_WARPS, MS_WARPS * 32, smem, (cudaStream_t)stream>>>(
+            P, tick, staged, h->n_sidx, h->n_ridx);
         CKL("match_search_kernel");
     }
     return VDS_OK;
