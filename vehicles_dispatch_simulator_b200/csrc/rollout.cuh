@@ -45,6 +45,16 @@ __device__ unsigned long long g_roll_prof[16];
 #define RPROF_END
 #endif
 
+// explicit 32-bit shared-window addressing for the hot scan: keeps the compiler from re-deriving the shared base
+// (S2R SR_CgaCtaId / LEA) and from predicating every load
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t smem_addr(const void *p) {
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("mov.u32 %0, %0;" : "+r"(a));                 // opaque: computed once, kept in a register
+    return a;
+}
+
 struct RollLayout {
     int key, ent, arrive, node, clus, icnt, ioff, wtot, ooff, acc, wl, wl_ix, wl_pd, wl_cnt, total;
 };
@@ -518,6 +528,7 @@ rollout_local_kernel(DevParams P, int k0, int nticks)
                 const bool small = n <= 32;
                 uint32_t e = ROLL_DEAD, ekey = ROLL_DEAD;
                 if (small && lane < n) { e = ent[i0 + lane]; ekey = key[e & 0xFFFF]; }
+                const uint32_t ent_sa = small ? 0u : smem_addr(ent + i0), key_sa = small ? 0u : smem_addr(key);
                 if (more && lane < m && lane > 0) { pdv = spd_t[b0 + lane]; idxv = sidx_t[b0 + lane]; }
                 int live = n;
                 for (int j = 0; j < m && live > 0; j++) {
@@ -539,24 +550,42 @@ rollout_local_kernel(DevParams P, int k0, int nticks)
                     if (small) {
                         if (e != ROLL_DEAD) cst = cost[rowoff + (e >> 16)];
                     } else {
-                        // branch-free: every live slot contributes (cost << 32 | idle key); 4 gathers in flight
+                        // long list, kept DENSE (a match swaps the last slot into the hole): no tombstone tests, the
+                        // tail is clamped instead of predicated, 4 gathers in flight, and every candidate is ONE
+                        // 64-bit word (cost:8 | idle key:32 | slot:16) whose minimum is the winner (Q5: keys are
+                        // unique, so the slot bits never decide).
+                        const int lm1 = live - 1;
+                        const uint8_t *row = cost + rowoff;
                         unsigned long long best = ~0ull;
-                        for (int q0 = lane; q0 < n; q0 += 128) {
-                            uint32_t t4[4], c4[4], k4[4];
+                        for (int q0 = lane; q0 <= lm1; q0 += 128) {
+                            uint32_t t4[4], c4[4], k4[4]; int q4[4];
 #pragma unroll
-                            for (int u = 0; u < 4; u++) { t4[u] = ROLL_DEAD; if (q0 + 32 * u < n) t4[u] = ent[i0 + q0 + 32 * u]; }
+                            for (int u = 0; u < 4; u++) { q4[u] = min(q0 + 32 * u, lm1); t4[u] = lds_u32(ent_sa + 4u * (uint32_t)q4[u]); }
 #pragma unroll
-                            for (int u = 0; u < 4; u++) {
-                                c4[u] = ROLL_DEAD; k4[u] = ROLL_DEAD;
-                                if (t4[u] != ROLL_DEAD) { c4[u] = cost[rowoff + (t4[u] >> 16)]; k4[u] = key[t4[u] & 0xFFFF]; }
-                            }
+                            for (int u = 0; u < 4; u++) { c4[u] = row[t4[u] >> 16]; k4[u] = lds_u32(key_sa + 4u * (t4[u] & 0xFFFFu)); }
 #pragma unroll
                             for (int u = 0; u < 4; u++) {
-                                const unsigned long long pk = ((unsigned long long)c4[u] << 32) | k4[u];
-                                if (pk < best) { best = pk; ex = t4[u]; idx = q0 + 32 * u; }
+                                const unsigned long long pk = ((unsigned long long)__funnelshift_l(k4[u], c4[u], 16) << 32)
+                                                              | (unsigned long long)((k4[u] << 16) | (uint32_t)q4[u]);
+                                best = pk < best ? pk : best;
                             }
                         }
-                        cst = (uint32_t)(best >> 32); bkey = (uint32_t)best;
+                        const uint32_t hi = (uint32_t)(best >> 32), lo = (uint32_t)best;
+                        if (lane == 0) t_look += (unsigned)live;
+                        const uint32_t hmin = __reduce_min_sync(FULL, hi);
+                        const uint32_t mn_l = hmin >> 16;
+                        if (mn_l > thr32) continue;                          // TempMin[1] > PICKUPTIMEWINDOW (:943): stays "Reject"
+                        const uint32_t lmin = __reduce_min_sync(FULL, hi == hmin ? lo : ROLL_DEAD);
+                        const uint32_t pos = lmin & 0xFFFFu;
+                        if (lane == 0) {
+                            const uint32_t wex = lds_u32(ent_sa + 4u * pos);
+                            cm.commit(wex, mn_l, o_val, dnode, o_dcl, o_idx);
+                            sts_u32(ent_sa + 4u * pos, lds_u32(ent_sa + 4u * (uint32_t)lm1));   // IdleVehicles.remove (:963)
+                            t_match++; t_wait += mn_l; t_val += o_val;
+                        }
+                        __syncwarp();
+                        live--;
+                        continue;
                     }
                     if (lane == 0) t_look += (unsigned)live;
                     const uint32_t mn = __reduce_min_sync(FULL, cst);
