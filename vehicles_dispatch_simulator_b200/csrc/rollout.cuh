@@ -55,9 +55,6 @@ __device__ __forceinline__ uint32_t smem_addr(const void *p) {
     return a;
 }
 
-struct RollLayout {
-    int key, ent, arrive, node, clus, icnt, ioff, wtot, ooff, acc, wl, wl_ix, wl_pd, wl_cnt, total;
-};
 __host__ __device__ inline RollLayout roll_layout(int Vp, int C)
 {
     const int Cp = (C + 3) & ~3;
@@ -279,7 +276,7 @@ rollout_local_kernel(DevParams P, int k0, int nticks)
     constexpr int NW = THREADS / 32;
     extern __shared__ __align__(16) unsigned char smraw[];
     const int Vp = P.Vp, C = P.C, Cp = (C + 3) & ~3;
-    const RollLayout L = roll_layout(Vp, C);
+    const RollLayout &L = P.L;                  // precomputed on the host: offsets come from the constant bank
     uint32_t *key = reinterpret_cast<uint32_t *>(smraw + L.key);
     uint32_t *ent = reinterpret_cast<uint32_t *>(smraw + L.ent);
     uint16_t *arrive = reinterpret_cast<uint16_t *>(smraw + L.arrive);

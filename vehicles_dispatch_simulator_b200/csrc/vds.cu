@@ -39,6 +39,10 @@
 #define UPD_THREADS 256
 #define UPD_WARPS (UPD_THREADS / 32)
 
+// shared-memory layout of rollout_local_kernel (rollout.cuh), computed once on the host
+struct RollLayout {
+    int key, ent, arrive, node, clus, icnt, ioff, wtot, ooff, acc, wl, wl_ix, wl_pd, wl_cnt, total;
+};
 struct DevParams {
     int R, V, Vp, C, nodes, Nmax, T, period, depth, ncs, OR, maxOT; unsigned period_magic;
     long long threshold;
@@ -49,6 +53,7 @@ struct DevParams {
     long long *stats; uint2 *idle_ent; int *idle_off, *bucket_off; uint16_t *bucket_ord; int *disp_seq;
     // derived order layout (vds_prepare_orders) + optional rollout trace
     const uint32_t *spd; const uint16_t *sord; const uint16_t *coff; const long long *tick_value; int *trace;
+    RollLayout L;
 };
 
 struct vds_handle_s {
@@ -850,7 +855,8 @@ int vds_create(const vds_config *cfg, vds_handle *out)
     { const char *e = getenv("VDS_FUSED_SEARCH"); h->fused_search = e && e[0] == '1'; }
     CK(cudaFuncSetAttribute(match_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     // replica-resident rollout kernel: pick the CTA width from how many replicas fit one SM
-    h->roll_smem = roll_layout(P.Vp, P.C).total;
+    P.L = roll_layout(P.Vp, P.C);
+    h->roll_smem = P.L.total;
     h->roll_threads = 0;
     if (h->roll_smem <= (int)prop.sharedMemPerBlockOptin) {
         const int per_sm = (int)prop.sharedMemPerMultiprocessor / (h->roll_smem + 1024);
