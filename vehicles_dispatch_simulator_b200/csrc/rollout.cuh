@@ -49,6 +49,7 @@ __device__ unsigned long long g_roll_prof[16];
 // (S2R SR_CgaCtaId / LEA) and from predicating every load
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" :: "r"(a), "h"((unsigned short)v) : "memory"); }
 __device__ __forceinline__ uint32_t smem_addr(const void *p) {
     uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
     asm volatile("mov.u32 %0, %0;" : "+r"(a));                 // opaque: computed once, kept in a register
@@ -110,8 +111,9 @@ __device__ __forceinline__ void block_scan_u32(const uint32_t *cnt, uint32_t *of
 }
 
 // commit of one match (simulator.py:946-965) on the shared-memory vehicle record
+// (shared arrays by 32-bit shared-window address: arrive, node, clus are consecutive u16[Vp] arrays)
 struct RollCommit {
-    uint16_t *arrive, *node, *clus; uint32_t *key; uint16_t *g_loc; uint32_t *res;
+    uint32_t arrive_sa, key_sa, stride; uint16_t *g_loc; uint32_t *res;
     int k, pm1; uint32_t magic;
     __device__ __forceinline__ void commit(uint32_t ex, uint32_t wait, int o_val, unsigned dnode, int o_dcl, int o_idx) const
     {
@@ -119,10 +121,11 @@ struct RollCommit {
         unsigned d = ((wait + (unsigned)o_val + (unsigned)pm1) * magic) >> 20;     // ceil((wait + value) / period), SURVEY Q6
         if (d < 1) d = 1;
         g_loc[v] = (uint16_t)(ex >> 16);                     // LocationNode unchanged until arrival (write-through)
-        arrive[v] = (uint16_t)((k + d) | 0x8000);
-        node[v] = (uint16_t)dnode;
-        clus[v] = (uint16_t)o_dcl;
-        key[v] = ((uint32_t)k << 21) | (uint32_t)o_idx;
+        const uint32_t a = arrive_sa + 2u * v;
+        sts_u16(a, (uint32_t)(k + d) | 0x8000u);             // arrive[v]
+        sts_u16(a + stride, dnode);                          // node[v]
+        sts_u16(a + 2u * stride, (uint32_t)o_dcl);           // clus[v]
+        sts_u32(key_sa + 4u * v, ((uint32_t)k << 21) | (uint32_t)o_idx);
         res[o_idx] = v | (wait << 16) | (d << 24);
     }
 };
@@ -131,7 +134,7 @@ struct RollCommit {
 // (order, vehicle) pairs are in flight at once, the greedy assignment runs in registers.
 // Kept out of line so its register footprint does not tax the warp-cooperative path.
 struct RollLane {
-    const uint32_t *ent, *key, *spd_t; const uint16_t *sidx_t, *n2c; const uint8_t *cost;
+    uint32_t ent_sa, key_sa; const uint32_t *spd_t; const uint16_t *sidx_t, *n2c; const uint8_t *cost;
     uint32_t nodes_u, thr32; int no_timeout;
 };
 __device__ __noinline__ uint4 roll_lane_match(RollLane q, RollCommit cm, int m_l, int n_l, int b0_l, int i0_l,
@@ -141,12 +144,12 @@ __device__ __noinline__ uint4 roll_lane_match(RollLane q, RollCommit cm, int m_l
     const int nord = q.no_timeout ? min(m_l, n_l) : m_l;              // orders that can still find a vehicle
     uint32_t e[4], kk[4], pd[4], cst[4][4]; int ix[4], val[4], dcl[4];
 #pragma unroll
-    for (int i = 0; i < 4; i++) { e[i] = ROLL_DEAD; if (i < n_l) e[i] = q.ent[i0_l + i]; }
+    for (int i = 0; i < 4; i++) { e[i] = ROLL_DEAD; if (i < n_l) e[i] = lds_u32(q.ent_sa + 4u * (uint32_t)(i0_l + i)); }
     pd[0] = pd0_l; ix[0] = idx0_l;
 #pragma unroll
     for (int j = 1; j < 4; j++) { pd[j] = 0; ix[j] = 0; if (j < nord) { pd[j] = q.spd_t[b0_l + j]; ix[j] = q.sidx_t[b0_l + j]; } }
 #pragma unroll
-    for (int i = 0; i < 4; i++) { kk[i] = ROLL_DEAD; if (i < n_l) kk[i] = q.key[e[i] & 0xFFFF]; }
+    for (int i = 0; i < 4; i++) { kk[i] = ROLL_DEAD; if (i < n_l) kk[i] = lds_u32(q.key_sa + 4u * (e[i] & 0xFFFFu)); }
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         val[j] = 0; dcl[j] = 0;
@@ -277,6 +280,8 @@ rollout_local_kernel(DevParams P, int k0, int nticks)
     extern __shared__ __align__(16) unsigned char smraw[];
     const int Vp = P.Vp, C = P.C, Cp = (C + 3) & ~3;
     const RollLayout &L = P.L;                  // precomputed on the host: offsets come from the constant bank
+    const uint32_t sm_sa = smem_addr(smraw);
+    const uint32_t arrive_sa0 = sm_sa + (uint32_t)L.arrive, key_sa0 = sm_sa + (uint32_t)L.key, ent_sa0 = sm_sa + (uint32_t)L.ent;
     uint32_t *key = reinterpret_cast<uint32_t *>(smraw + L.key);
     uint32_t *ent = reinterpret_cast<uint32_t *>(smraw + L.ent);
     uint16_t *arrive = reinterpret_cast<uint16_t *>(smraw + L.arrive);
@@ -473,10 +478,10 @@ rollout_local_kernel(DevParams P, int k0, int nticks)
         const uint32_t *spd_t = spd_base + tb;
         const uint16_t *sidx_t = sidx_base + tb;
         RollCommit cm;
-        cm.arrive = arrive; cm.node = node; cm.clus = clus; cm.key = key; cm.g_loc = P.veh_loc + vb;
+        cm.arrive_sa = arrive_sa0; cm.key_sa = key_sa0; cm.stride = 2u * (uint32_t)Vp; cm.g_loc = P.veh_loc + vb;
         cm.res = res_base + tb; cm.k = k; cm.magic = P.period_magic; cm.pm1 = P.period - 1;
         RollLane lq;
-        lq.ent = ent; lq.key = key; lq.spd_t = spd_t; lq.sidx_t = sidx_t; lq.n2c = n2c; lq.cost = cost;
+        lq.ent_sa = ent_sa0; lq.key_sa = key_sa0; lq.spd_t = spd_t; lq.sidx_t = sidx_t; lq.n2c = n2c; lq.cost = cost;
         lq.nodes_u = nodes_u; lq.thr32 = thr32; lq.no_timeout = no_timeout ? 1 : 0;
         if constexpr (!SEARCH) {
         // -- 6a: every thread classifies clusters (orders this tick? idle vehicles?) and files the active ones,
@@ -525,7 +530,7 @@ rollout_local_kernel(DevParams P, int k0, int nticks)
                 const bool small = n <= 32;
                 uint32_t e = ROLL_DEAD, ekey = ROLL_DEAD;
                 if (small && lane < n) { e = ent[i0 + lane]; ekey = key[e & 0xFFFF]; }
-                const uint32_t ent_sa = small ? 0u : smem_addr(ent + i0), key_sa = small ? 0u : smem_addr(key);
+                const uint32_t ent_sa = ent_sa0 + 4u * (uint32_t)i0, key_sa = key_sa0;
                 if (more && lane < m && lane > 0) { pdv = spd_t[b0 + lane]; idxv = sidx_t[b0 + lane]; }
                 int live = n;
                 for (int j = 0; j < m && live > 0; j++) {
