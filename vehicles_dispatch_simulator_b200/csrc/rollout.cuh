@@ -393,17 +393,21 @@ rollout_local_kernel(DevParams P, int k0, int nticks)
             RPROF(11)
             __syncthreads();
             RPROF(12)
+            // two u16 per 32-bit op: (0x8000 + k) - (t & 0x7FFF) keeps bit 15 iff (t & 0x7FFF) <= k, and never borrows
+            // into the neighbouring half; idle (0xFFFF) and padding (0x7FFF) entries have 0x7FFF > k.
+            const uint32_t k2 = ((uint32_t)k | 0x8000u) * 0x00010001u;
             for (int g = tid; g < ngroups; g += THREADS) {
-                U16x8 a; a.v = reinterpret_cast<uint4 *>(arrive)[g];
-                unsigned arriving = 0;
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const unsigned t = a.h[j];
-                    if (t != IDLE16 && (int)(t & 0x7FFF) <= k) arriving |= 1u << j;
-                }
-                while (arriving) {
-                    const int j = __ffs(arriving) - 1; arriving &= arriving - 1;
-                    ent[atomicAdd(&wl_cnt[3], 1u)] = (uint32_t)(g * 8 + j);
+                const uint4 a = reinterpret_cast<const uint4 *>(arrive)[g];
+                const uint32_t f0 = (k2 - (a.x & 0x7FFF7FFFu)) & 0x80008000u, f1 = (k2 - (a.y & 0x7FFF7FFFu)) & 0x80008000u;
+                const uint32_t f2 = (k2 - (a.z & 0x7FFF7FFFu)) & 0x80008000u, f3 = (k2 - (a.w & 0x7FFF7FFFu)) & 0x80008000u;
+                if (f0 | f1 | f2 | f3) {
+                    // bit i: low half of word i (vehicle 2i), bit 16 + i: high half (vehicle 2i + 1)
+                    uint32_t b = (f0 >> 15) | (f1 >> 14) | (f2 >> 13) | (f3 >> 12);
+                    while (b) {
+                        const int p = __ffs(b) - 1; b &= b - 1;
+                        const int j = p < 16 ? 2 * p : 2 * (p - 16) + 1;
+                        ent[atomicAdd(&wl_cnt[3], 1u)] = (uint32_t)(g * 8 + j);
+                    }
                 }
             }
             RPROF(13)
