@@ -516,7 +516,10 @@ rollout_local_kernel(DevParams P, int k0, int nticks)
             }
         }
         RPROF(7)
-        // -- 6b: warps pop clusters off the work list: lanes over the cluster's idle slots
+        // -- 6b: warps pop clusters off the work list: lanes over the cluster's idle slots.  The winner of order j is
+        //    only RECORDED by the lane that holds that order (lane j % 32); the commits (RoadCost(pickup, delivery),
+        //    destination cluster, vehicle record, result word) run lane-parallel once per 32 orders of the cluster,
+        //    off the sequential chain.
         {
             const int n_work = (int)wl_cnt[0];
             while (true) {
@@ -525,36 +528,49 @@ rollout_local_kernel(DevParams P, int k0, int nticks)
                 slot = __shfl_sync(FULL, slot, 0);
                 if (slot >= n_work) break;
                 const int c = wl[slot];
-                const uint32_t pd0 = wl_pd[slot]; const int idx0 = wl_ix[slot];
                 const int b0 = ooff[c], m = (int)ooff[c + 1] - b0;
                 const int n = (int)icnt[c], i0 = (int)ioff[c] - n;
-                // orders 1.. of this cluster (only needed while vehicles remain): issue now, use later
-                uint32_t pdv = 0; int idxv = 0;
-                const bool more = m > 1 && (n > 1 || !no_timeout);     // a timeout reject does not consume a vehicle
+                const int steps = no_timeout ? min(m, n) : m;           // a timeout reject does not consume a vehicle
+                // lane l holds order (chunk base + l) of this cluster; order 0 was fetched by the classifier
+                uint32_t pdv = wl_pd[slot]; int idxv = wl_ix[slot];
+                if (lane > 0 && lane < steps) { pdv = spd_t[b0 + lane]; idxv = sidx_t[b0 + lane]; }
                 const bool small = n <= 32;
                 uint32_t e = ROLL_DEAD, ekey = ROLL_DEAD;
                 if (small && lane < n) { e = ent[i0 + lane]; ekey = key[e & 0xFFFF]; }
                 const uint32_t ent_sa = ent_sa0 + 4u * (uint32_t)i0, key_sa = key_sa0;
-                if (more && lane < m && lane > 0) { pdv = spd_t[b0 + lane]; idxv = sidx_t[b0 + lane]; }
-                int live = n;
-                for (int j = 0; j < m && live > 0; j++) {
-                    uint32_t o_pd; int o_idx;
-                    if (j == 0) { o_pd = pd0; o_idx = idx0; }
-                    else {
-                        if ((j & 31) == 0) {                             // next chunk of the cluster's orders
-                            pdv = 0; idxv = 0;
-                            if (j + lane < m) { pdv = spd_t[b0 + j + lane]; idxv = sidx_t[b0 + j + lane]; }
-                        }
-                        o_pd = __shfl_sync(FULL, pdv, j & 31); o_idx = __shfl_sync(FULL, idxv, j & 31);
+                uint32_t my_ex = ROLL_DEAD, my_wait = 0;                // winner of THIS lane's order, committed by flush()
+                auto flush = [&]() {
+                    if (my_ex != ROLL_DEAD) {
+                        const unsigned pnode = pdv & 0xFFFF, dnode = pdv >> 16;
+                        const int o_val = cost[dnode * nodes_u + pnode];             // RoadCost(pickup, delivery) (:341-342)
+                        cm.commit(my_ex, my_wait, o_val, dnode, (int)n2c[dnode], idxv);
+                        t_match++; t_wait += my_wait; t_val += (unsigned)o_val;
+                        my_ex = ROLL_DEAD;
                     }
-                    const unsigned pnode = o_pd & 0xFFFF, dnode = o_pd >> 16;
-                    const uint32_t rowoff = pnode * nodes_u;                     // RoadCost(loc, pickup) = cost[pickup][loc]
-                    const int o_val = cost[dnode * nodes_u + pnode];             // RoadCost(pickup, delivery) (:341-342)
-                    const int o_dcl = n2c[dnode];
-                    uint32_t cst = ROLL_DEAD, ex = e; int idx = 0;
-                    uint32_t bkey = ekey;
+                };
+                int live = n;
+                for (int j = 0; j < steps && live > 0; j++) {
+                    if ((j & 31) == 0 && j > 0) {                        // next 32 orders of the cluster
+                        flush();
+                        pdv = 0; idxv = 0;
+                        if (j + lane < steps) { pdv = spd_t[b0 + j + lane]; idxv = sidx_t[b0 + j + lane]; }
+                    }
+                    const uint32_t rowoff = (__shfl_sync(FULL, pdv, j & 31) & 0xFFFF) * nodes_u;   // RoadCost(loc, pickup) = cost[pickup][loc]
+                    if (lane == 0) t_look += (unsigned)live;
                     if (small) {
+                        uint32_t cst = ROLL_DEAD;
                         if (e != ROLL_DEAD) cst = cost[rowoff + (e >> 16)];
+                        const uint32_t mn = __reduce_min_sync(FULL, cst);
+                        if (mn > thr32) continue;                            // TempMin[1] > PICKUPTIMEWINDOW (:943): stays "Reject"
+                        unsigned tied = __ballot_sync(FULL, cst == mn);
+                        if (tied & (tied - 1)) {                             // cost tie: first in IdleVehicles order wins (Q5)
+                            const uint32_t kmin = __reduce_min_sync(FULL, cst == mn ? ekey : ROLL_DEAD);
+                            tied = __ballot_sync(FULL, cst == mn && ekey == kmin);
+                        }
+                        const int win = __ffs(tied) - 1;
+                        const uint32_t wex = __shfl_sync(FULL, e, win);
+                        if (lane == (j & 31)) { my_ex = wex; my_wait = mn; }
+                        if (lane == win) e = ROLL_DEAD;                      // IdleVehicles.remove (:963)
                     } else {
                         // long list, kept DENSE (a match swaps the last slot into the hole): no tombstone tests, the
                         // tail is clamped instead of predicated, 4 gathers in flight, and every candidate is ONE
@@ -577,38 +593,20 @@ rollout_local_kernel(DevParams P, int k0, int nticks)
                             }
                         }
                         const uint32_t hi = (uint32_t)(best >> 32), lo = (uint32_t)best;
-                        if (lane == 0) t_look += (unsigned)live;
                         const uint32_t hmin = __reduce_min_sync(FULL, hi);
-                        const uint32_t mn_l = hmin >> 16;
-                        if (mn_l > thr32) continue;                          // TempMin[1] > PICKUPTIMEWINDOW (:943): stays "Reject"
+                        const uint32_t mn = hmin >> 16;
+                        if (mn > thr32) continue;                            // TempMin[1] > PICKUPTIMEWINDOW (:943): stays "Reject"
                         const uint32_t lmin = __reduce_min_sync(FULL, hi == hmin ? lo : ROLL_DEAD);
                         const uint32_t pos = lmin & 0xFFFFu;
-                        if (lane == 0) {
-                            const uint32_t wex = lds_u32(ent_sa + 4u * pos);
-                            cm.commit(wex, mn_l, o_val, dnode, o_dcl, o_idx);
-                            sts_u32(ent_sa + 4u * pos, lds_u32(ent_sa + 4u * (uint32_t)lm1));   // IdleVehicles.remove (:963)
-                            t_match++; t_wait += mn_l; t_val += o_val;
-                        }
+                        const uint32_t wex = lds_u32(ent_sa + 4u * pos);     // same address in every lane
                         __syncwarp();
-                        live--;
-                        continue;
+                        if (lane == 0) sts_u32(ent_sa + 4u * pos, lds_u32(ent_sa + 4u * (uint32_t)lm1));   // IdleVehicles.remove (:963)
+                        if (lane == (j & 31)) { my_ex = wex; my_wait = mn; }
+                        __syncwarp();
                     }
-                    if (lane == 0) t_look += (unsigned)live;
-                    const uint32_t mn = __reduce_min_sync(FULL, cst);
-                    if (mn > thr32) continue;                                // TempMin[1] > PICKUPTIMEWINDOW (:943): stays "Reject"
-                    unsigned tied = __ballot_sync(FULL, cst == mn);
-                    if (tied & (tied - 1)) {                                 // cost tie: first in IdleVehicles order wins (Q5)
-                        const uint32_t kmin = __reduce_min_sync(FULL, cst == mn ? bkey : ROLL_DEAD);
-                        tied = __ballot_sync(FULL, cst == mn && bkey == kmin);
-                    }
-                    if (lane == __ffs(tied) - 1) {
-                        cm.commit(ex, mn, o_val, dnode, o_dcl, o_idx);
-                        if (small) e = ROLL_DEAD; else ent[i0 + idx] = ROLL_DEAD;   // IdleVehicles.remove (:963)
-                        t_match++; t_wait += mn; t_val += o_val;
-                    }
-                    if (!small) __syncwarp();
                     live--;
                 }
+                flush();
                 if (lane == 0) icnt[c] = (uint32_t)live;                     // len(IdleVehicles) after the match phase
             }
         }
