@@ -76,6 +76,7 @@ __host__ __device__ inline RollLayout roll_layout(int Vp, int C)
     L.wl_pd = o;  o += 4 * Cp;
     L.wl = o;     o += 2 * Cp;
     L.wl_ix = o;  o += 2 * Cp;
+    L.wla = o;    o += 2 * Cp;                                  // clusters with a single idle vehicle (pass 6s)
     if (o - L.wl_pd < 6 * 128) o = L.wl_pd + 6 * 128;        // search variant: 6 x u32[32] speculation records alias this region
     L.total = (o + 15) & ~15;
     return L;
@@ -296,6 +297,7 @@ rollout_local_kernel(DevParams P, int k0, int nticks)
     uint32_t *wl_cnt = reinterpret_cast<uint32_t *>(smraw + L.wl_cnt);
     uint16_t *wl = reinterpret_cast<uint16_t *>(smraw + L.wl);
     uint16_t *wl_ix = reinterpret_cast<uint16_t *>(smraw + L.wl_ix);
+    uint16_t *wla = reinterpret_cast<uint16_t *>(smraw + L.wla);
 
     const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const size_t vb = (size_t)r * Vp;
@@ -496,14 +498,48 @@ rollout_local_kernel(DevParams P, int k0, int nticks)
             const int n_l = (int)icnt[c_l];
             if (m_l > 0 && n_l > 0) {
                 const uint32_t pd0_l = spd_t[b0_l]; const int idx0_l = sidx_t[b0_l];
-                const bool lp = n_l <= 4 && (no_timeout || m_l <= 4);
-                const int slot = lp ? C - 1 - (int)atomicAdd(&wl_cnt[1], 1u) : (int)atomicAdd(&wl_cnt[0], 1u);
-                wl[slot] = (uint16_t)c_l; wl_pd[slot] = pd0_l; wl_ix[slot] = (uint16_t)idx0_l;
+                if (n_l == 1 && no_timeout) {
+                    // the most common active cluster (59 % on the Didi-shaped workload) has ONE idle vehicle.  Without a
+                    // timeout its first order takes it (:921-934, 946-965): no argmin.  Narrow CTAs (many replicas per
+                    // SM hide the latency) settle it right here with the order already fetched; wide CTAs (one
+                    // replica per SM, cost table beyond L2) queue it for a dense pass with all gathers in flight.
+                    if constexpr (THREADS == 128) {
+                        const uint32_t e1 = ent[ioff[c_l] - 1];
+                        const unsigned pn = pd0_l & 0xFFFF, dn = pd0_l >> 16;
+                        const uint32_t wait = cost[pn * nodes_u + (e1 >> 16)];   // RoadCost(loc, pickup) = cost[pickup][loc]
+                        const int o_val = cost[dn * nodes_u + pn];               // RoadCost(pickup, delivery) (:341-342)
+                        cm.commit(e1, wait, o_val, dn, (int)n2c[dn], idx0_l);
+                        t_match++; t_wait += wait; t_val += (unsigned)o_val; t_look++;
+                        icnt[c_l] = 0;                                           // len(IdleVehicles) after the match phase
+                    } else {
+                        wla[atomicAdd(&wl_cnt[3], 1u)] = (uint16_t)c_l;
+                    }
+                } else {
+                    const bool lp = n_l <= 4 && (no_timeout || m_l <= 4);
+                    const int slot = lp ? C - 1 - (int)atomicAdd(&wl_cnt[1], 1u) : (int)atomicAdd(&wl_cnt[0], 1u);
+                    wl[slot] = (uint16_t)c_l; wl_pd[slot] = pd0_l; wl_ix[slot] = (uint16_t)idx0_l;
+                }
             }
         }
         RPROF(5)
         __syncthreads();
         RPROF(6)
+        // -- 6s: dense pass over the queued single-vehicle clusters (wide CTAs only, see 6a)
+        if constexpr (THREADS != 128) {
+            const int n_s = (int)wl_cnt[3];
+            for (int i = tid; i < n_s; i += THREADS) {
+                const int c_l = wla[i];
+                const int b0_l = ooff[c_l];
+                const uint32_t pd0_l = spd_t[b0_l]; const int idx0_l = sidx_t[b0_l];
+                const uint32_t e1 = ent[ioff[c_l] - 1];
+                const unsigned pn = pd0_l & 0xFFFF, dn = pd0_l >> 16;
+                const uint32_t wait = cost[pn * nodes_u + (e1 >> 16)];           // RoadCost(loc, pickup) = cost[pickup][loc]
+                const int o_val = cost[dn * nodes_u + pn];                       // RoadCost(pickup, delivery) (:341-342)
+                cm.commit(e1, wait, o_val, dn, (int)n2c[dn], idx0_l);
+                t_match++; t_wait += wait; t_val += (unsigned)o_val; t_look++;
+                icnt[c_l] = 0;                                                   // len(IdleVehicles) after the match phase
+            }
+        }
         {
             const int n_lp = (int)wl_cnt[1];
             for (int i = tid; i < n_lp; i += THREADS) {                  // dense: no idle lanes between small clusters

@@ -41,7 +41,7 @@
 
 // shared-memory layout of rollout_local_kernel (rollout.cuh), computed once on the host
 struct RollLayout {
-    int key, ent, arrive, node, clus, icnt, ioff, wtot, ooff, acc, wl, wl_ix, wl_pd, wl_cnt, total;
+    int key, ent, arrive, node, clus, icnt, ioff, wtot, ooff, acc, wl, wl_ix, wl_pd, wl_cnt, wla, total;
 };
 struct DevParams {
     int R, V, Vp, C, nodes, Nmax, T, period, depth, ncs, OR, maxOT; unsigned period_magic;
