@@ -208,6 +208,8 @@ def main():
     ap.add_argument("--replicas", type=int, default=None, help="replicas per GPU (default: the workload's)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--policy-per-tick", action="store_true",
+                    help="config4: run the Dispatch hook as separate per-tick launches instead of fused into the rollout kernel")
     args = ap.parse_args()
 
     import torch
@@ -262,7 +264,10 @@ def main():
     policy = w.get("policy")
 
     def run_ticks():
-        if policy:      # hook every tick: one fused tick launch + policy kernel + dispatch primitive per time slot
+        if policy and eng.fused and not args.policy_per_tick:
+            # the device-resident hook fused into the replica-resident kernel: one launch per episode
+            eng.rollout_policy_random(0, T, seed=SEED, first_replica=shard.first_replica, prob=policy)
+        elif policy:    # hook every tick: one fused tick launch + policy kernel + dispatch primitive per time slot
             for k in range(T):
                 eng.tick(k)
                 eng.policy_random_dispatch(k, seed=SEED, first_replica=shard.first_replica, prob=policy)
@@ -359,7 +364,18 @@ def main():
     # ---- per-kernel device times (CUDA events on the launch stream) and the roofline of the dominant kernel
     V, Cn = eng.V, eng.nC
     peak, peak_src = measured_peak_gbs()
-    if policy:
+    if policy and eng.fused and not args.policy_per_tick:
+        evs = []
+        for _ in range(max(3, args.steps)):
+            eng.reset(loc0)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); run_ticks(); b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize(dev)
+        kt = {"rollout+policy": float(np.mean([a.elapsed_time(b) for a, b in evs]))}   # ms per launch
+        dom, launches_per_episode = "rollout+policy", 1
+        kname = "rollout_local_kernel<%d,local,policy>" % eng.rollout_threads
+    elif policy:
         names = ("tick", "policy+dispatch")
         evs = {n: [] for n in names}
         eng.reset(loc0)
@@ -408,7 +424,10 @@ def main():
     if policy:
         bytes_k["policy+dispatch"] = 2.0 * V * R * T + 20.0 * D          # idle flags read + (move record + vehicle record) per move
         b_total = sum(bytes_k.values())
-    b_dom = (b_total - bytes_k.get("policy+dispatch", 0.0)) if eng.fused else bytes_k["match"]
+    if dom == "rollout+policy":
+        b_dom = b_total                                                    # one kernel does the tick AND the hook
+    else:
+        b_dom = (b_total - bytes_k.get("policy+dispatch", 0.0)) if eng.fused else bytes_k["match"]
     ach = b_dom / (kt[dom] * 1e-3) / 1e9
     roof = {"bound": "hbm", "kernel": kname,
             "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak,

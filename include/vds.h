@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define VDS_ABI_VERSION 2
+#define VDS_ABI_VERSION 3
 
 typedef enum vds_status {
     VDS_OK = 0,
@@ -205,6 +205,15 @@ int  vds_dispatch_strided(vds_handle h, int tick, const int32_t *move_cnt, const
 int  vds_policy_random(vds_handle h, int tick, uint64_t seed, int64_t first_replica, uint32_t move_prob_q32,
                        const int32_t *nb_off, const uint16_t *nb_idx, const int32_t *cl_node_off, const uint16_t *cl_nodes,
                        int32_t *move_cnt, int32_t *move_veh, int32_t *move_node, int stride, void *stream);
+
+/* The same hook FUSED into the replica-resident rollout kernel: ticks [tick0, tick0+nticks), each followed by
+ * the random dispatch policy of vds_policy_random + the dispatch primitive (same Philox draws, same move
+ * numbering, bit-identical state) -- one launch for the whole window instead of three launches per tick.
+ * Needs prepared orders and the own-cluster match (neighbor_can_server == 0 or depth_limit == 0); returns
+ * VDS_ERR_UNBOUND otherwise (callers then run vds_tick + vds_policy_random + vds_dispatch_strided per tick). */
+int  vds_rollout_policy_random(vds_handle h, int tick0, int nticks, uint64_t seed, int64_t first_replica,
+                               uint32_t move_prob_q32, const int32_t *nb_off, const uint16_t *nb_idx,
+                               const int32_t *cl_node_off, const uint16_t *cl_nodes, void *stream);
 
 /* Hook-free ticks [tick0, tick0+nticks): update, match, supply_expect per tick
  * (the body of SimCity's loop, simulator.py:1048-1091, with empty hooks).

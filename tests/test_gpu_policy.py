@@ -56,3 +56,45 @@ def test_device_random_policy_lockstep(cuda_device, ncs, service, prob):
         assert tuple(st[r][:6]) == tuple(o.stats()[:6]), f"{st[r]} vs {o.stats()}"
     # replicas differ (keyed by global id) and the split does not matter
     assert not np.array_equal(st[0][:6], st[1][:6])
+
+
+@pytest.mark.parametrize("V,prob,windows", [(500, 0.3, None), (500, 0.05, [1, 2, 5, 0]), (2600, 0.2, None), (9000, 0.1, [3, 0])])
+def test_fused_policy_rollout_equals_per_tick(cuda_device, V, prob, windows):
+    """vds_rollout_policy_random (the hook fused into the replica-resident kernel: ONE launch per window) leaves
+    bit-identical state, results and counters to the per-tick path tick -> policy kernel -> dispatch primitive, which
+    the test above pins to the oracle.  128-, 256- and 512-thread CTA variants; window boundaries."""
+    from vehicles_dispatch_simulator_b200.engine import DispatchEngine, tick_offsets
+    from vehicles_dispatch_simulator_b200.synthetic import synthetic_grid_city
+    rng = np.random.default_rng(V)
+    city = synthetic_grid_city(side_m=800, service_m=800, neighbor_can_server=False, n_nodes=700)
+    R, seed, first = 3, 7, 1000
+    minute, pick, drop = random_orders(city, 6000, rng)
+    off, T = tick_offsets(minute, 10)
+    loc0 = rng.choice(city.valid_nodes(), (R, V)).astype(np.int32)
+
+    def make():
+        e = DispatchEngine(city, V, replicas=R, ticks=T, max_orders=len(minute), max_orders_per_tick=int(np.diff(off).max()))
+        e.bind_shared_orders(minute, pick, drop)
+        e.reset(loc0)
+        return e
+
+    a, b = make(), make()
+    for k in range(T):
+        a.tick(k)
+        a.policy_random_dispatch(k, seed=seed, first_replica=first, prob=prob)
+    if windows:
+        windows = list(windows); windows[-1] = T - sum(windows)
+        k = 0
+        for n in windows:
+            b.rollout_policy_random(k, n, seed=seed, first_replica=first, prob=prob); k += n
+    else:
+        b.rollout_policy_random(0, T, seed=seed, first_replica=first, prob=prob)
+    sa, sb = a.stats().cpu().numpy(), b.stats().cpu().numpy()
+    assert sa[:, 4].min() > 50                                          # the policy did move vehicles
+    assert np.array_equal(sa, sb), f"{sa} vs {sb}"
+    for name in ("veh_loc", "veh_cluster", "veh_arrive", "veh_dest", "veh_key", "per_match", "per_dispatch", "idle_live",
+                 "supply", "n_orders", "disp_seq"):
+        assert np.array_equal(a.tensors[name].cpu().numpy(), b.tensors[name].cpu().numpy()), name
+    n = len(minute) - 1
+    assert np.array_equal(a.tensors["order_res"][:, :n].cpu().numpy(), b.tensors["order_res"][:, :n].cpu().numpy())
+    a.close(); b.close()

@@ -57,7 +57,7 @@ class State(C.Structure):
 # every symbol include/vds.h declares (tests check the export list against this)
 EXPORTS = ("vds_abi_version", "vds_padded_vehicles", "vds_create", "vds_destroy", "vds_last_error",
            "vds_bind_static", "vds_bind_orders", "vds_bind_state", "vds_compute_order_values",
-           "vds_prepare_orders", "vds_reset", "vds_clear_results", "vds_update", "vds_match", "vds_supply_expect", "vds_dispatch", "vds_dispatch_strided", "vds_policy_random", "vds_rollout", "vds_tick", "vds_rollout_is_fused", "vds_rollout_threads",
+           "vds_prepare_orders", "vds_reset", "vds_clear_results", "vds_update", "vds_match", "vds_supply_expect", "vds_dispatch", "vds_dispatch_strided", "vds_policy_random", "vds_rollout_policy_random", "vds_rollout", "vds_tick", "vds_rollout_is_fused", "vds_rollout_threads",
            "vds_stats", "vds_sync", "vds_launch_count", "vds_generate_orders", "vds_generate_placement")
 
 
@@ -106,6 +106,7 @@ def lib():
         "vds_dispatch": (C.c_int, [vp, i32, vp, vp, vp, i32, vp]),
         "vds_dispatch_strided": (C.c_int, [vp, i32, vp, vp, vp, i32, vp]),
         "vds_policy_random": (C.c_int, [vp, i32, u64, i64, C.c_uint32, vp, vp, vp, vp, vp, vp, vp, i32, vp]),
+        "vds_rollout_policy_random": (C.c_int, [vp, i32, i32, u64, i64, C.c_uint32, vp, vp, vp, vp, vp]),
         "vds_rollout": (C.c_int, [vp, i32, i32, vp]),
         "vds_tick": (C.c_int, [vp, i32, vp]),
         "vds_rollout_is_fused": (C.c_int, [vp]),

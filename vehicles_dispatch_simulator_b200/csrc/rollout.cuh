@@ -273,9 +273,9 @@ __device__ __forceinline__ RollPick roll_search_pick(const uint32_t *ent, const 
     return r;
 }
 
-template <int THREADS, int MINB, bool SEARCH>
+template <int THREADS, int MINB, bool SEARCH, bool POLICY>
 __global__ void __launch_bounds__(THREADS, MINB)
-rollout_local_kernel(DevParams P, int k0, int nticks)
+rollout_local_kernel(DevParams P, int k0, int nticks, RollPolicy pol)
 {
     constexpr int NW = THREADS / 32;
     extern __shared__ __align__(16) unsigned char smraw[];
@@ -336,6 +336,8 @@ rollout_local_kernel(DevParams P, int k0, int nticks)
     const bool no_timeout = P.threshold >= 255;       // cost bytes are <= 255: "cost > threshold" can never fire
     const uint32_t thr32 = P.threshold > 0xFFFFFFF0LL ? 0xFFFFFFF0u : (P.threshold < 0 ? 0u : (uint32_t)P.threshold);
     long long a_orders = 0, a_tickval = 0;          // thread 0 only
+    unsigned a_dnum = 0; unsigned long long a_dcost = 0;   // fused dispatch policy (POLICY)
+    int last_moves = 0;
     __syncthreads();
     RPROF_DECL
 
@@ -758,6 +760,86 @@ rollout_local_kernel(DevParams P, int k0, int nticks)
             for (int i = tid; i < C; i += THREADS) { g_s[i] = (int)ioff[i]; if (tr) tr[2 * C + i] = (int)ioff[i]; }
             __syncthreads();
         }
+
+        // ---- phase 8 (POLICY): the DispatchFunction hook of this tick, resident on the device (simulator.py:1083,
+        //      BASELINE config 4): every idle vehicle moves with probability p to a uniformly drawn node of a
+        //      uniformly drawn neighbour cluster -- the same draws as policy_random_kernel (Philox keyed by seed and
+        //      GLOBAL replica id, counter (vehicle, tick)) applied with the semantics of dispatch_kernel: moves are
+        //      numbered in vehicle-index order (insertion order of the reference's VehiclesArrivetime dicts).
+        if constexpr (POLICY && !SEARCH) {
+            const unsigned long long g = (unsigned long long)(pol.first_replica + r);
+            int run = 0;                                             // moves of earlier rounds
+            for (int vbase = 0; vbase < Vp; vbase += THREADS * 16) {
+                const int v0 = vbase + tid * 16;
+                uint32_t dec[8];                                     // two target nodes per word, 0xFFFF = stay
+#pragma unroll
+                for (int i = 0; i < 8; i++) dec[i] = 0xFFFFFFFFu;
+                int cnt = 0;
+                if (v0 < Vp) {
+                    U16x8 a0, a1; a0.v = reinterpret_cast<const uint4 *>(arrive)[v0 >> 3]; a1.v = reinterpret_cast<const uint4 *>(arrive)[(v0 >> 3) + 1];
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        const unsigned t = j < 8 ? a0.h[j] : a1.h[j - 8];
+                        if (t == IDLE16) {
+                            const int v = v0 + j;
+                            const Philox x = philox4x32_10((uint32_t)v, (3u << 16) | (uint32_t)k, (uint32_t)g, (uint32_t)(g >> 32),
+                                                           (uint32_t)pol.seed, (uint32_t)(pol.seed >> 32));
+                            if (x.c[0] < pol.prob_q32) {
+                                const int c = clus[v];
+                                const int n0 = pol.nb_off[c], deg = pol.nb_off[c + 1] - n0;
+                                if (deg > 0) {
+                                    const int tc = pol.nb_idx[n0 + (int)(((uint64_t)x.c[1] * (uint64_t)deg) >> 32)];
+                                    const int c0 = pol.cl_node_off[tc], nn = pol.cl_node_off[tc + 1] - c0;
+                                    if (nn > 0) {
+                                        const uint32_t nd = pol.cl_nodes[c0 + (int)(((uint64_t)x.c[2] * (uint64_t)nn) >> 32)];
+                                        dec[j >> 1] = (j & 1) ? ((dec[j >> 1] & 0x0000FFFFu) | (nd << 16)) : ((dec[j >> 1] & 0xFFFF0000u) | nd);
+                                        cnt++;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+                // exclusive block scan of cnt: move index in vehicle order
+                int incl = cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += t; }
+                if (lane == 31) wtot[w] = (uint32_t)incl;
+                __syncthreads();
+                int before = run + incl - cnt, total = 0;
+#pragma unroll
+                for (int ww = 0; ww < NW; ww++) { const int t = (int)wtot[ww]; if (ww < w) before += t; total += t; }
+                run += total;
+                if (cnt) {
+                    int idx = before;
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        const uint32_t nd = (j & 1) ? (dec[j >> 1] >> 16) : (dec[j >> 1] & 0xFFFFu);
+                        if (nd != 0xFFFFu) {
+                            const int v = v0 + j;
+                            const uint32_t loc = node[v];                                // idle: LocationNode
+                            const uint32_t cst = cost[nd * nodes_u + loc];               // RoadCost(loc, node)
+                            unsigned d = ((cst + (unsigned)(P.period - 1)) * P.period_magic) >> 20; if (d < 1) d = 1;
+                            const int src = clus[v];
+                            P.veh_loc[vb + v] = (uint16_t)loc;                           // LocationNode unchanged until arrival
+                            arrive[v] = (uint16_t)(k + d);                               // no order on board (bit 15 clear)
+                            node[v] = (uint16_t)nd;
+                            clus[v] = n2c[nd];
+                            key[v] = ((uint32_t)k << 21) | (uint32_t)(16384 + (idx & 16383));
+                            atomicSub(&icnt[src], 1u);
+                            a_dnum++; a_dcost += cst; idx++;
+                        }
+                    }
+                }
+                __syncthreads();                                     // wtot reused by the next round / next tick
+            }
+            last_moves = run;
+            if (emit) {                                              // LaterDispatchIdleVehicles (:1086-1087)
+                __syncthreads();
+                int *g_lv = P.idle_live + (size_t)r * C;
+                for (int i = tid; i < C; i += THREADS) g_lv[i] = (int)icnt[i];
+            }
+        }
     }
 
     RPROF(10)
@@ -794,6 +876,11 @@ rollout_local_kernel(DevParams P, int k0, int nticks)
         }
         const unsigned arr_w = __reduce_add_sync(FULL, a_arrive);
         if (lane == 0) atomicAdd(&acc[4], (unsigned long long)arr_w);
+        if constexpr (POLICY) {
+            const unsigned dn_w = __reduce_add_sync(FULL, a_dnum);
+            for (int d = 16; d; d >>= 1) a_dcost += __shfl_xor_sync(FULL, a_dcost, d);
+            if (lane == 0) { atomicAdd(&acc[5], (unsigned long long)dn_w); atomicAdd(&acc[6], a_dcost); }
+        }
         __syncthreads();
         if (tid == 0) {
             long long *st = P.stats + (size_t)r * VDS_NUM_STATS;
@@ -806,7 +893,8 @@ rollout_local_kernel(DevParams P, int k0, int nticks)
             st[VDS_STAT_ARRIVALS] += (long long)acc[4];
             st[VDS_STAT_MATCHES] += matches;
             st[VDS_STAT_TICKS] += nticks;
-            P.disp_seq[r] = 0;
+            if constexpr (POLICY) { st[VDS_STAT_DISPATCH_NUM] += (long long)acc[5]; st[VDS_STAT_DISPATCH_COST] += (long long)acc[6]; }
+            P.disp_seq[r] = POLICY ? last_moves : 0;
         }
     }
 }

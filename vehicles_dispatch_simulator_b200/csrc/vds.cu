@@ -655,9 +655,7 @@ __global__ void order_value_kernel(DevParams P, const uint32_t *opd, const int *
     if ((threadIdx.x & 31) == 0 && s) atomicAddLL(vtotal + ro, s);
 }
 
-#include "rollout.cuh"
-
-// ------------------------------------------- synthetic Didi-shaped generator
+// Philox4x32-10 counter RNG (generators, device-resident policy)
 struct Philox { uint32_t c[4]; };
 __host__ __device__ inline Philox philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1)
 {
@@ -670,6 +668,15 @@ __host__ __device__ inline Philox philox4x32_10(uint32_t c0, uint32_t c1, uint32
     }
     Philox r; r.c[0] = c0; r.c[1] = c1; r.c[2] = c2; r.c[3] = c3; return r;
 }
+// Device-resident DispatchFunction hook fused into the rollout kernel (vds_rollout_policy_random)
+struct RollPolicy {
+    unsigned long long seed; long long first_replica; uint32_t prob_q32;
+    const int *nb_off; const uint16_t *nb_idx; const int *cl_node_off; const uint16_t *cl_nodes;
+};
+
+#include "rollout.cuh"
+
+// ------------------------------------------- synthetic Didi-shaped generator
 // smallest j with u < cdf[j]  (cdf non-decreasing, cdf[n-1] == 0xFFFFFFFF catches everything)
 __device__ __forceinline__ int cdf_search(const uint32_t *cdf, int n, uint32_t u)
 {
@@ -861,12 +868,15 @@ int vds_create(const vds_config *cfg, vds_handle *out)
     if (h->roll_smem <= (int)prop.sharedMemPerBlockOptin) {
         const int per_sm = (int)prop.sharedMemPerMultiprocessor / (h->roll_smem + 1024);
         h->roll_threads = per_sm >= 6 ? 128 : per_sm >= 3 ? 256 : 512;
-        CK(cudaFuncSetAttribute(rollout_local_kernel<128, 7, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
-        CK(cudaFuncSetAttribute(rollout_local_kernel<256, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
-        CK(cudaFuncSetAttribute(rollout_local_kernel<512, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
-        CK(cudaFuncSetAttribute(rollout_local_kernel<128, 7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
-        CK(cudaFuncSetAttribute(rollout_local_kernel<256, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
-        CK(cudaFuncSetAttribute(rollout_local_kernel<512, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
+        CK(cudaFuncSetAttribute(rollout_local_kernel<128, 7, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
+        CK(cudaFuncSetAttribute(rollout_local_kernel<256, 3, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
+        CK(cudaFuncSetAttribute(rollout_local_kernel<512, 1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
+        CK(cudaFuncSetAttribute(rollout_local_kernel<128, 7, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
+        CK(cudaFuncSetAttribute(rollout_local_kernel<256, 3, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
+        CK(cudaFuncSetAttribute(rollout_local_kernel<512, 1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
+        CK(cudaFuncSetAttribute(rollout_local_kernel<128, 7, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
+        CK(cudaFuncSetAttribute(rollout_local_kernel<256, 3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
+        CK(cudaFuncSetAttribute(rollout_local_kernel<512, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
     }
     return VDS_OK;
 }
@@ -1077,15 +1087,15 @@ int vds_rollout(vds_handle h, int tick0, int nticks, void *stream)
         cudaStream_t st = (cudaStream_t)stream;
         if (local_mode(h)) {
             switch (h->roll_threads) {
-            case 128: rollout_local_kernel<128, 7, false><<<h->P.R, 128, h->roll_smem, st>>>(h->P, tick0, nticks); break;
-            case 256: rollout_local_kernel<256, 3, false><<<h->P.R, 256, h->roll_smem, st>>>(h->P, tick0, nticks); break;
-            default:  rollout_local_kernel<512, 1, false><<<h->P.R, 512, h->roll_smem, st>>>(h->P, tick0, nticks); break;
+            case 128: rollout_local_kernel<128, 7, false, false><<<h->P.R, 128, h->roll_smem, st>>>(h->P, tick0, nticks, RollPolicy()); break;
+            case 256: rollout_local_kernel<256, 3, false, false><<<h->P.R, 256, h->roll_smem, st>>>(h->P, tick0, nticks, RollPolicy()); break;
+            default:  rollout_local_kernel<512, 1, false, false><<<h->P.R, 512, h->roll_smem, st>>>(h->P, tick0, nticks, RollPolicy()); break;
             }
         } else {
             switch (h->roll_threads) {
-            case 128: rollout_local_kernel<128, 7, true><<<h->P.R, 128, h->roll_smem, st>>>(h->P, tick0, nticks); break;
-            case 256: rollout_local_kernel<256, 3, true><<<h->P.R, 256, h->roll_smem, st>>>(h->P, tick0, nticks); break;
-            default:  rollout_local_kernel<512, 1, true><<<h->P.R, 512, h->roll_smem, st>>>(h->P, tick0, nticks); break;
+            case 128: rollout_local_kernel<128, 7, true, false><<<h->P.R, 128, h->roll_smem, st>>>(h->P, tick0, nticks, RollPolicy()); break;
+            case 256: rollout_local_kernel<256, 3, true, false><<<h->P.R, 256, h->roll_smem, st>>>(h->P, tick0, nticks, RollPolicy()); break;
+            default:  rollout_local_kernel<512, 1, true, false><<<h->P.R, 512, h->roll_smem, st>>>(h->P, tick0, nticks, RollPolicy()); break;
             }
         }
         CKL("rollout_local_kernel");
@@ -1100,6 +1110,29 @@ int vds_rollout(vds_handle h, int tick0, int nticks, void *stream)
 }
 
 int vds_tick(vds_handle h, int tick, void *stream) { return vds_rollout(h, tick, 1, stream); }
+
+int vds_rollout_policy_random(vds_handle h, int tick0, int nticks, uint64_t seed, int64_t first_replica,
+                              uint32_t move_prob_q32, const int32_t *nb_off, const uint16_t *nb_idx,
+                              const int32_t *cl_node_off, const uint16_t *cl_nodes, void *stream)
+{
+    int rc = ready(h, true); if (rc) return rc;
+    if (tick0 < 0 || nticks < 0 || tick0 + nticks > h->P.T) return fail(h, VDS_ERR_INVALID, "vds_rollout_policy_random: tick range");
+    if (!nb_off || !nb_idx || !cl_node_off || !cl_nodes) return fail(h, VDS_ERR_INVALID, "vds_rollout_policy_random: null pointer");
+    if (!(h->prepared && h->roll_threads > 0 && local_mode(h)))
+        return fail(h, VDS_ERR_UNBOUND, "vds_rollout_policy_random: needs prepared orders and the own-cluster (depth 0) match; "
+                                      "use vds_tick + vds_policy_random + vds_dispatch_strided per tick otherwise");
+    if (nticks == 0) return VDS_OK;
+    RollPolicy pol; pol.seed = seed; pol.first_replica = first_replica; pol.prob_q32 = move_prob_q32;
+    pol.nb_off = nb_off; pol.nb_idx = nb_idx; pol.cl_node_off = cl_node_off; pol.cl_nodes = cl_nodes;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (h->roll_threads) {
+    case 128: rollout_local_kernel<128, 7, false, true><<<h->P.R, 128, h->roll_smem, st>>>(h->P, tick0, nticks, pol); break;
+    case 256: rollout_local_kernel<256, 3, false, true><<<h->P.R, 256, h->roll_smem, st>>>(h->P, tick0, nticks, pol); break;
+    default:  rollout_local_kernel<512, 1, false, true><<<h->P.R, 512, h->roll_smem, st>>>(h->P, tick0, nticks, pol); break;
+    }
+    CKL("rollout_local_kernel<policy>");
+    return VDS_OK;
+}
 
 int vds_stats(vds_handle h, int64_t *out, void *stream)
 {

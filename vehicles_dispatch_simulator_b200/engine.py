@@ -300,9 +300,7 @@ class DispatchEngine:
             return
         self._ck(self.L.vds_dispatch(self.h, int(k), _ptr(mo), _ptr(mv), _ptr(mn), int(mv.numel()), self._stream()))
 
-    def policy_random_dispatch(self, k, seed=1234, first_replica=0, prob=0.05):
-        """Device-resident random DispatchFunction hook (BASELINE config 4) + the dispatch primitive for tick k:
-        every idle vehicle moves with probability `prob` to a random node of a random neighbour cluster."""
+    def _policy_tables(self):
         if getattr(self, "_pol", None) is None:
             city, dev = self.city, self.device
             nodes = city.cluster_nodes if city.cluster_nodes is not None else \
@@ -315,7 +313,24 @@ class DispatchEngine:
                              cnt=torch.zeros(self.R, dtype=torch.int32, device=dev),
                              veh=torch.zeros((self.R, self.Vp), dtype=torch.int32, device=dev),
                              node=torch.zeros((self.R, self.Vp), dtype=torch.int32, device=dev))
-        p = self._pol
+        return self._pol
+
+    def rollout_policy_random(self, tick0=0, nticks=None, seed=1234, first_replica=0, prob=0.05):
+        """Ticks [tick0, tick0+nticks) with the device-resident random DispatchFunction hook after every tick,
+        FUSED into the replica-resident rollout kernel: one launch, bit-identical to
+        `for k: tick(k); policy_random_dispatch(k, ...)`.  Depth-0 engines only (VdsError otherwise)."""
+        nticks = self.T - tick0 if nticks is None else nticks
+        p = self._policy_tables()
+        q32 = min(0xFFFFFFFF, int(prob * 4294967296.0))
+        self._ck(self.L.vds_rollout_policy_random(self.h, int(tick0), int(nticks), C.c_uint64(seed), C.c_int64(first_replica),
+                                                  C.c_uint32(q32), _ptr(p["nb_off"]), _ptr(p["nb_idx"]), _ptr(p["noff"]),
+                                                  _ptr(p["nflat"]), self._stream()))
+        self._done_upto = max(self._done_upto, int(tick0) + int(nticks))
+
+    def policy_random_dispatch(self, k, seed=1234, first_replica=0, prob=0.05):
+        """Device-resident random DispatchFunction hook (BASELINE config 4) + the dispatch primitive for tick k:
+        every idle vehicle moves with probability `prob` to a random node of a random neighbour cluster."""
+        p = self._policy_tables()
         q32 = min(0xFFFFFFFF, int(prob * 4294967296.0))
         self._ck(self.L.vds_policy_random(self.h, int(k), C.c_uint64(seed), C.c_int64(first_replica), C.c_uint32(q32),
                                           _ptr(p["nb_off"]), _ptr(p["nb_idx"]), _ptr(p["noff"]), _ptr(p["nflat"]),
