@@ -771,17 +771,13 @@ rollout_local_kernel(DevParams P, int k0, int nticks, RollPolicy pol)
             int run = 0;                                             // moves of earlier rounds
             for (int vbase = 0; vbase < Vp; vbase += THREADS * 16) {
                 const int v0 = vbase + tid * 16;
-                uint32_t dec[8];                                     // two target nodes per word, 0xFFFF = stay
-#pragma unroll
-                for (int i = 0; i < 8; i++) dec[i] = 0xFFFFFFFFu;
-                int cnt = 0;
+                // pass A (rolled: the Philox body exists once in the instruction stream): which of my 16 vehicles move
+                uint32_t mask = 0;
                 if (v0 < Vp) {
-                    U16x8 a0, a1; a0.v = reinterpret_cast<const uint4 *>(arrive)[v0 >> 3]; a1.v = reinterpret_cast<const uint4 *>(arrive)[(v0 >> 3) + 1];
-#pragma unroll
+#pragma unroll 1
                     for (int j = 0; j < 16; j++) {
-                        const unsigned t = j < 8 ? a0.h[j] : a1.h[j - 8];
-                        if (t == IDLE16) {
-                            const int v = v0 + j;
+                        const int v = v0 + j;
+                        if (arrive[v] == IDLE16) {
                             const Philox x = philox4x32_10((uint32_t)v, (3u << 16) | (uint32_t)k, (uint32_t)g, (uint32_t)(g >> 32),
                                                            (uint32_t)pol.seed, (uint32_t)(pol.seed >> 32));
                             if (x.c[0] < pol.prob_q32) {
@@ -789,17 +785,13 @@ rollout_local_kernel(DevParams P, int k0, int nticks, RollPolicy pol)
                                 const int n0 = pol.nb_off[c], deg = pol.nb_off[c + 1] - n0;
                                 if (deg > 0) {
                                     const int tc = pol.nb_idx[n0 + (int)(((uint64_t)x.c[1] * (uint64_t)deg) >> 32)];
-                                    const int c0 = pol.cl_node_off[tc], nn = pol.cl_node_off[tc + 1] - c0;
-                                    if (nn > 0) {
-                                        const uint32_t nd = pol.cl_nodes[c0 + (int)(((uint64_t)x.c[2] * (uint64_t)nn) >> 32)];
-                                        dec[j >> 1] = (j & 1) ? ((dec[j >> 1] & 0x0000FFFFu) | (nd << 16)) : ((dec[j >> 1] & 0xFFFF0000u) | nd);
-                                        cnt++;
-                                    }
+                                    if (pol.cl_node_off[tc + 1] - pol.cl_node_off[tc] > 0) mask |= 1u << j;
                                 }
                             }
                         }
                     }
                 }
+                const int cnt = __popc(mask);
                 // exclusive block scan of cnt: move index in vehicle order
                 int incl = cnt;
 #pragma unroll
@@ -810,26 +802,28 @@ rollout_local_kernel(DevParams P, int k0, int nticks, RollPolicy pol)
 #pragma unroll
                 for (int ww = 0; ww < NW; ww++) { const int t = (int)wtot[ww]; if (ww < w) before += t; total += t; }
                 run += total;
-                if (cnt) {
-                    int idx = before;
-#pragma unroll
-                    for (int j = 0; j < 16; j++) {
-                        const uint32_t nd = (j & 1) ? (dec[j >> 1] >> 16) : (dec[j >> 1] & 0xFFFFu);
-                        if (nd != 0xFFFFu) {
-                            const int v = v0 + j;
-                            const uint32_t loc = node[v];                                // idle: LocationNode
-                            const uint32_t cst = cost[nd * nodes_u + loc];               // RoadCost(loc, node)
-                            unsigned d = ((cst + (unsigned)(P.period - 1)) * P.period_magic) >> 20; if (d < 1) d = 1;
-                            const int src = clus[v];
-                            P.veh_loc[vb + v] = (uint16_t)loc;                           // LocationNode unchanged until arrival
-                            arrive[v] = (uint16_t)(k + d);                               // no order on board (bit 15 clear)
-                            node[v] = (uint16_t)nd;
-                            clus[v] = n2c[nd];
-                            key[v] = ((uint32_t)k << 21) | (uint32_t)(16384 + (idx & 16383));
-                            atomicSub(&icnt[src], 1u);
-                            a_dnum++; a_dcost += cst; idx++;
-                        }
-                    }
+                // pass B: the movers (a few per cent) draw again and go
+                int idx = before;
+                while (mask) {
+                    const int j = __ffs(mask) - 1; mask &= mask - 1;
+                    const int v = v0 + j;
+                    const Philox x = philox4x32_10((uint32_t)v, (3u << 16) | (uint32_t)k, (uint32_t)g, (uint32_t)(g >> 32),
+                                                   (uint32_t)pol.seed, (uint32_t)(pol.seed >> 32));
+                    const int src = clus[v];
+                    const int n0 = pol.nb_off[src], deg = pol.nb_off[src + 1] - n0;
+                    const int tc = pol.nb_idx[n0 + (int)(((uint64_t)x.c[1] * (uint64_t)deg) >> 32)];
+                    const int c0 = pol.cl_node_off[tc], nn = pol.cl_node_off[tc + 1] - c0;
+                    const uint32_t nd = pol.cl_nodes[c0 + (int)(((uint64_t)x.c[2] * (uint64_t)nn) >> 32)];
+                    const uint32_t loc = node[v];                                        // idle: LocationNode
+                    const uint32_t cst = cost[nd * nodes_u + loc];                       // RoadCost(loc, node)
+                    unsigned d = ((cst + (unsigned)(P.period - 1)) * P.period_magic) >> 20; if (d < 1) d = 1;
+                    P.veh_loc[vb + v] = (uint16_t)loc;                                   // LocationNode unchanged until arrival
+                    arrive[v] = (uint16_t)(k + d);                                       // no order on board (bit 15 clear)
+                    node[v] = (uint16_t)nd;
+                    clus[v] = n2c[nd];
+                    key[v] = ((uint32_t)k << 21) | (uint32_t)(16384 + (idx & 16383));
+                    atomicSub(&icnt[src], 1u);
+                    a_dnum++; a_dcost += cst; idx++;
                 }
                 __syncthreads();                                     // wtot reused by the next round / next tick
             }
