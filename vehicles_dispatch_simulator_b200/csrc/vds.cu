@@ -867,10 +867,14 @@ int vds_create(const vds_config *cfg, vds_handle *out)
     h->roll_threads = 0;
     if (h->roll_smem <= (int)prop.sharedMemPerBlockOptin) {
         const int per_sm = (int)prop.sharedMemPerMultiprocessor / (h->roll_smem + 1024);
-        h->roll_threads = per_sm >= 6 ? 128 : per_sm >= 3 ? 256 : 512;
+        h->roll_threads = per_sm >= 6 ? 128 : per_sm >= 3 ? 256 : per_sm >= 2 ? 512 : 1024;   // one replica per SM: all 32 warps on it
+        { const char *e = getenv("VDS_ROLL_THREADS");       // developer knob: force a CTA width
+          if (e && (atoi(e) == 128 || atoi(e) == 256 || atoi(e) == 512 || atoi(e) == 1024)) h->roll_threads = atoi(e); }
         CK(cudaFuncSetAttribute(rollout_local_kernel<128, 7, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
         CK(cudaFuncSetAttribute(rollout_local_kernel<256, 3, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
         CK(cudaFuncSetAttribute(rollout_local_kernel<512, 1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
+        CK(cudaFuncSetAttribute(rollout_local_kernel<1024, 1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
+        CK(cudaFuncSetAttribute(rollout_local_kernel<1024, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
         CK(cudaFuncSetAttribute(rollout_local_kernel<128, 7, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
         CK(cudaFuncSetAttribute(rollout_local_kernel<256, 3, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
         CK(cudaFuncSetAttribute(rollout_local_kernel<512, 1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
@@ -1089,10 +1093,11 @@ int vds_rollout(vds_handle h, int tick0, int nticks, void *stream)
             switch (h->roll_threads) {
             case 128: rollout_local_kernel<128, 7, false, false><<<h->P.R, 128, h->roll_smem, st>>>(h->P, tick0, nticks, RollPolicy()); break;
             case 256: rollout_local_kernel<256, 3, false, false><<<h->P.R, 256, h->roll_smem, st>>>(h->P, tick0, nticks, RollPolicy()); break;
+            case 1024: rollout_local_kernel<1024, 1, false, false><<<h->P.R, 1024, h->roll_smem, st>>>(h->P, tick0, nticks, RollPolicy()); break;
             default:  rollout_local_kernel<512, 1, false, false><<<h->P.R, 512, h->roll_smem, st>>>(h->P, tick0, nticks, RollPolicy()); break;
             }
         } else {
-            switch (h->roll_threads) {
+            switch (h->roll_threads == 1024 ? 512 : h->roll_threads) {
             case 128: rollout_local_kernel<128, 7, true, false><<<h->P.R, 128, h->roll_smem, st>>>(h->P, tick0, nticks, RollPolicy()); break;
             case 256: rollout_local_kernel<256, 3, true, false><<<h->P.R, 256, h->roll_smem, st>>>(h->P, tick0, nticks, RollPolicy()); break;
             default:  rollout_local_kernel<512, 1, true, false><<<h->P.R, 512, h->roll_smem, st>>>(h->P, tick0, nticks, RollPolicy()); break;
@@ -1128,6 +1133,7 @@ int vds_rollout_policy_random(vds_handle h, int tick0, int nticks, uint64_t seed
     switch (h->roll_threads) {
     case 128: rollout_local_kernel<128, 7, false, true><<<h->P.R, 128, h->roll_smem, st>>>(h->P, tick0, nticks, pol); break;
     case 256: rollout_local_kernel<256, 3, false, true><<<h->P.R, 256, h->roll_smem, st>>>(h->P, tick0, nticks, pol); break;
+    case 1024: rollout_local_kernel<1024, 1, false, true><<<h->P.R, 1024, h->roll_smem, st>>>(h->P, tick0, nticks, pol); break;
     default:  rollout_local_kernel<512, 1, false, true><<<h->P.R, 512, h->roll_smem, st>>>(h->P, tick0, nticks, pol); break;
     }
     CKL("rollout_local_kernel<policy>");
