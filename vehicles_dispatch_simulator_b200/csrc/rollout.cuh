@@ -570,7 +570,8 @@ rollout_local_kernel(DevParams P, int k0, int nticks, RollPolicy pol)
                 const int n = (int)icnt[c], i0 = (int)ioff[c] - n;
                 const int steps = no_timeout ? min(m, n) : m;           // a timeout reject does not consume a vehicle
                 // lane l holds order (chunk base + l) of this cluster; order 0 was fetched by the classifier
-                uint32_t pdv = wl_pd[slot]; int idxv = wl_ix[slot];
+                const uint32_t pdv0 = wl_pd[slot];
+                uint32_t pdv = pdv0; int idxv = wl_ix[slot];
                 if (lane > 0 && lane < steps) { pdv = spd_t[b0 + lane]; idxv = sidx_t[b0 + lane]; }
                 const bool small = n <= 32;
                 uint32_t e = ROLL_DEAD, ekey = ROLL_DEAD;
@@ -587,17 +588,25 @@ rollout_local_kernel(DevParams P, int k0, int nticks, RollPolicy pol)
                     }
                 };
                 int live = n;
+                // short lists: the cost gather of order j + 1 is issued before order j is resolved (the slot a lane
+                // holds never changes, it can only die), so the sequential chain is REDUX -> ballot, not gather -> REDUX
+                // (matters when the cost table does not fit L2: 768-grid city, 274 MB)
+                uint32_t cnext = ROLL_DEAD;
+                if (small && e != ROLL_DEAD) cnext = cost[(pdv0 & 0xFFFF) * nodes_u + (e >> 16)];
                 for (int j = 0; j < steps && live > 0; j++) {
                     if ((j & 31) == 0 && j > 0) {                        // next 32 orders of the cluster
                         flush();
                         pdv = 0; idxv = 0;
                         if (j + lane < steps) { pdv = spd_t[b0 + j + lane]; idxv = sidx_t[b0 + j + lane]; }
+                        if (small && e != ROLL_DEAD) cnext = cost[(__shfl_sync(FULL, pdv, 0) & 0xFFFF) * nodes_u + (e >> 16)];
                     }
-                    const uint32_t rowoff = (__shfl_sync(FULL, pdv, j & 31) & 0xFFFF) * nodes_u;   // RoadCost(loc, pickup) = cost[pickup][loc]
                     if (lane == 0) t_look += (unsigned)live;
                     if (small) {
-                        uint32_t cst = ROLL_DEAD;
-                        if (e != ROLL_DEAD) cst = cost[rowoff + (e >> 16)];
+                        const uint32_t cst = e != ROLL_DEAD ? cnext : ROLL_DEAD;
+                        if (j + 1 < steps && ((j + 1) & 31) != 0) {
+                            const uint32_t rown = (__shfl_sync(FULL, pdv, (j + 1) & 31) & 0xFFFF) * nodes_u;   // RoadCost(loc, pickup) = cost[pickup][loc]
+                            if (e != ROLL_DEAD) cnext = cost[rown + (e >> 16)];
+                        }
                         const uint32_t mn = __reduce_min_sync(FULL, cst);
                         if (mn > thr32) continue;                            // TempMin[1] > PICKUPTIMEWINDOW (:943): stays "Reject"
                         unsigned tied = __ballot_sync(FULL, cst == mn);
@@ -615,7 +624,7 @@ rollout_local_kernel(DevParams P, int k0, int nticks, RollPolicy pol)
                         // 64-bit word (cost:8 | idle key:32 | slot:16) whose minimum is the winner (Q5: keys are
                         // unique, so the slot bits never decide).
                         const int lm1 = live - 1;
-                        const uint8_t *row = cost + rowoff;
+                        const uint8_t *row = cost + (__shfl_sync(FULL, pdv, j & 31) & 0xFFFF) * nodes_u;   // RoadCost(loc, pickup) = cost[pickup][loc]
                         unsigned long long best = ~0ull;
                         for (int q0 = lane; q0 <= lm1; q0 += 128) {
                             uint32_t t4[4], c4[4], k4[4]; int q4[4];
