@@ -70,7 +70,8 @@ def measured_traffic(workload, kernel):
 
 
 class ClockSampler:
-    """SM clock + throttle reasons DURING the timed region: NVML polled every 2 ms from a thread
+    """SM clock + throttle reasons DURING the timed region: NVML polled every 10 ms from a thread (a 2 ms period
+    costs the launching thread ~0.5 ms per step under NCCL through the GIL)
     (nvidia-smi -lms as fallback; its first sample can arrive after a short timed region has ended)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -123,7 +124,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(float(os.environ.get("BENCH_CLOCK_PERIOD_S", "0.01")))
 
     def _read_smi(self):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -198,7 +199,31 @@ def cpu_port_run(city, eng, loc0, tables, sample_replicas, budget_s, threads, or
     return ticks / wall, wall, rounds, oracles
 
 
+_JSON_FD = None
+
+
+def _stdout_only_for_the_json_line():
+    """stdout must carry exactly ONE line (the JSON).  Libraries write to fd 1 behind Python's back -- NCCL prints
+    "NCCL version ..." there when NCCL_DEBUG asks for it -- so fd 1 is pointed at stderr for the whole run and the
+    JSON line goes to a private duplicate of the original stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_json(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, data)
+
+
 def main():
+    _stdout_only_for_the_json_line()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -248,7 +273,7 @@ def main():
                                  "sample": f"{S} replicas x {tables.ticks} ticks per step, C port of the reference loop, {cores} threads"},
                 "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "cluster_ticks_per_sec": value * city.n_clusters}
-        print(json.dumps(line))
+        emit_json(line)
         return 0
 
     # ----------------------------------------------------------------- our arm
@@ -287,6 +312,10 @@ def main():
 
     for _ in range(args.warmup):
         ret = episode()
+    if world > 1:                      # NCCL sets channels up lazily: settle the collective before anything is timed
+        for _ in range(8):
+            shard.all_gather_returns(eng.stats())
+            dist.barrier()
     barrier()
     # ---- timed region: EXACTLY K steps, device-timed on the launching stream
     clocks = ClockSampler(local_rank) if rank == 0 else None
@@ -474,7 +503,7 @@ def main():
                                                 "re-prepared every step"},
                 "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
                 "parity_check_vs_oracle": parity}
-        print(json.dumps(line))
+        emit_json(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
