@@ -363,8 +363,8 @@ match_local_kernel(DevParams P, int k)
 // one warp; replicas are the parallel dimension.
 // The search lists and their inverses (read on every order's dependent chain) are staged in shared memory
 // once per CTA when they fit (`staged`; sizes from vds_bind_static).
-#define MS_WARPS 8
-__global__ void __launch_bounds__(MS_WARPS * 32)
+#define MS_WARPS 7          // 7 warps x 4 CTAs = 28 warps/SM: 4096 replicas are one wave on 148 SMs at 72 registers, no spills
+__global__ void __launch_bounds__(MS_WARPS * 32, 4)
 match_search_kernel(DevParams P, int k, int staged, int n_sidx, int n_ridx)
 {
     extern __shared__ int sm[];
