@@ -102,6 +102,10 @@ __device__ void block_exclusive_scan(const int *cnt, int *off, int C, int *warp_
     __syncthreads();
 }
 
+// Makes a pointer opaque to the optimiser: it is computed ONCE and kept in registers instead of being
+// re-derived from kernel parameters / blockIdx at every use (ptxas prefers rematerialisation under pressure).
+template <typename T> __device__ __forceinline__ T *keep(T *p) { asm volatile("" : "+l"(p)); return p; }
+
 union U16x8 { uint4 v; uint16_t h[8]; };
 union U32x4 { uint4 v; uint32_t w[4]; };
 
@@ -408,9 +412,10 @@ match_search_kernel(DevParams P, int k, int staged, int n_sidx, int n_ridx)
     const int tb = toff[k], n = toff[k + 1] - tb;
     const uint32_t *opd = P.opd + (size_t)ro * P.Nmax + tb;
     const uint8_t *oval = P.oval + (size_t)ro * P.Nmax + tb;
-    uint32_t *res = P.order_res + (size_t)r * P.Nmax + tb;
-    uint2 *ent = P.idle_ent + (size_t)r * P.Vp;
+    uint32_t *res = keep(P.order_res + (size_t)r * P.Nmax + tb);
+    uint2 *ent = keep(P.idle_ent + (size_t)r * P.Vp);
     const size_t vb = (size_t)r * P.Vp;
+    const uint8_t *cost = keep(P.cost);
 
     int rej = 0, rejval = 0, matches = 0; long long wait_sum = 0; int my_lookups = 0;
 
@@ -445,7 +450,7 @@ match_search_kernel(DevParams P, int k, int staged, int n_sidx, int n_ridx)
 #pragma unroll
                     for (int u = 0; u < 2; u++) if (q0 + 32 * u < own) t2[u] = ent[i0 + q0 + 32 * u];
 #pragma unroll
-                    for (int u = 0; u < 2; u++) if (q0 + 32 * u < own) c2[u] = P.cost[rowoff + (t2[u].x >> 16)];
+                    for (int u = 0; u < 2; u++) if (q0 + 32 * u < own) c2[u] = cost[rowoff + (t2[u].x >> 16)];
 #pragma unroll
                     for (int u = 0; u < 2; u++) if (q0 + 32 * u < own) offer(t2[u], c2[u], 0, i0 + q0 + 32 * u);
                 }
@@ -484,7 +489,7 @@ match_search_kernel(DevParams P, int k, int staged, int n_sidx, int n_ridx)
                         if (jj < total) {
                             const int wh = p_i0 + (jj - (p_incl - p_nn));
                             const uint2 t = ent[wh];
-                            offer(t, P.cost[rowoff + (t.x >> 16)], (uint32_t)p_sp, wh);
+                            offer(t, cost[rowoff + (t.x >> 16)], (uint32_t)p_sp, wh);
                         }
                     }
                     __syncwarp();
