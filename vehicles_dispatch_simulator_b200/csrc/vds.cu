@@ -427,8 +427,11 @@ match_search_kernel(DevParams P, int k, int staged, int n_sidx, int n_ridx)
         // (idle sets only shrink inside a tick): settle all of those of the chunk at once
         const bool dead_l = lane < cnt && reach[oc] == 0;
         unsigned todo = __ballot_sync(FULL, lane < cnt && !dead_l);
-        if (dead_l) res[base + lane] = 0x0000FFFFu;
         rej += __popc(__ballot_sync(FULL, dead_l)); rejval += __reduce_add_sync(FULL, dead_l ? val : 0);
+        // lane l keeps the outcome of order base + l ("Reject" until matched); the vehicle record and the result
+        // words of the whole chunk are written lane-parallel after the sequential part (nothing in this kernel
+        // reads them back), only the slot removal and the counters stay on the per-order chain
+        uint32_t my_v = DEAD32, my_mn = 0;
         while (todo) {
             const int j = __ffs(todo) - 1; todo &= todo - 1;
             const uint32_t o_pd = __shfl_sync(FULL, pd, j);
@@ -499,7 +502,6 @@ match_search_kernel(DevParams P, int k, int staged, int n_sidx, int n_ridx)
             const uint32_t hmin = __reduce_min_sync(FULL, hi);                     // (cost, search position)
             const uint32_t mn = hmin == DEAD32 ? DEAD32 : hmin >> 16;
             if (mn == DEAD32 || (long long)mn > P.threshold) {
-                if (lane == 0) res[base + j] = 0x0000FFFFu;
                 rej++; rejval += o_val;
                 continue;
             }
@@ -511,15 +513,9 @@ match_search_kernel(DevParams P, int k, int staged, int n_sidx, int n_ridx)
             const int win = __ffs(tied) - 1;
             const uint32_t spos = hmin & 0xFFFF;
             const int src = spos ? (int)sidx[soff[c] + spos] : c;
+            const uint32_t wex = __shfl_sync(FULL, ex, win);
+            if (lane == j) { my_v = wex & 0xFFFF; my_mn = mn; }
             if (lane == win) {
-                const int v = ex & 0xFFFF;
-                int d = (int)((((uint32_t)mn + (uint32_t)o_val + (uint32_t)P.period - 1u) * P.period_magic) >> 20); if (d < 1) d = 1;
-                const int dnode = o_pd >> 16;
-                P.veh_arrive[vb + v] = (uint16_t)((k + d) | 0x8000);
-                P.veh_dest[vb + v] = (uint16_t)dnode;
-                P.veh_cluster[vb + v] = P.n2c[dnode];
-                P.veh_key[vb + v] = ((uint32_t)k << 21) | (uint32_t)(base + j);
-                res[base + j] = (uint32_t)v | (mn << 16) | ((uint32_t)d << 24);
                 const int last = ioff[src] + live[src] - 1;                         // IdleVehicles.remove (:963): keep the slots compact
                 if (idx != last) ent[idx] = ent[last];
                 live[src] -= 1;
@@ -527,6 +523,19 @@ match_search_kernel(DevParams P, int k, int staged, int n_sidx, int n_ridx)
             for (int q = roff[src] + lane; q < roff[src + 1]; q += 32) reach[ridx[q]] -= 1;
             __syncwarp();
             matches++; wait_sum += mn;
+        }
+        if (lane < cnt) {                                                           // commit the chunk (simulator.py:946-969)
+            uint32_t word = 0x0000FFFFu;                                            // ArriveInfo = "Reject"
+            if (my_v != DEAD32) {
+                int d = (int)((((uint32_t)my_mn + (uint32_t)val + (uint32_t)P.period - 1u) * P.period_magic) >> 20); if (d < 1) d = 1;
+                const int dnode = pd >> 16;
+                P.veh_arrive[vb + my_v] = (uint16_t)((k + d) | 0x8000);
+                P.veh_dest[vb + my_v] = (uint16_t)dnode;
+                P.veh_cluster[vb + my_v] = P.n2c[dnode];
+                P.veh_key[vb + my_v] = ((uint32_t)k << 21) | (uint32_t)(base + lane);
+                word = my_v | (my_mn << 16) | ((uint32_t)d << 24);
+            }
+            res[base + lane] = word;
         }
     }
     {
