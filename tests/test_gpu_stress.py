@@ -1,7 +1,9 @@
 """-m gpu: randomised configurations of the replica-resident rollout kernel against the oracle -- vehicle counts
 around the packing boundaries (Vp multiple of 8, 2048-slot and CTA-width switches), skewed pickups (very long idle
 lists in a few clusters, single-vehicle clusters everywhere else), timeout thresholds, random window boundaries,
-distinct placements per replica.  VDS_STRESS_CASES widens the sweep (default 6 cases, ~10 s)."""
+distinct placements per replica.  VDS_STRESS_CASES widens the sweep (default 24 cases + the regressions, ~5 s).
+Case 211 (coarse grid, timeout 3, > 32 orders in a cluster with <= 32 idle vehicles) once dead-locked the kernel: a
+warp shuffle sat behind a per-lane condition at the 32-order chunk boundary."""
 import os
 
 import numpy as np
@@ -11,10 +13,12 @@ from tests.helpers import make_oracle, random_orders, rollout_vs_oracle
 
 pytestmark = pytest.mark.gpu
 
-N_CASES = int(os.environ.get("VDS_STRESS_CASES", "6"))
+N_CASES = int(os.environ.get("VDS_STRESS_CASES", "24"))
+CASES = sorted(set(range(N_CASES)) | {211})
 
 
-@pytest.mark.parametrize("case", range(N_CASES))
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("case", CASES)
 def test_random_rollout_configuration(cuda_device, case):
     from vehicles_dispatch_simulator_b200.engine import DispatchEngine, tick_offsets
     from vehicles_dispatch_simulator_b200.synthetic import synthetic_grid_city

@@ -598,7 +598,8 @@ rollout_local_kernel(DevParams P, int k0, int nticks, RollPolicy pol)
                         flush();
                         pdv = 0; idxv = 0;
                         if (j + lane < steps) { pdv = spd_t[b0 + j + lane]; idxv = sidx_t[b0 + j + lane]; }
-                        if (small && e != ROLL_DEAD) cnext = cost[(__shfl_sync(FULL, pdv, 0) & 0xFFFF) * nodes_u + (e >> 16)];
+                        const uint32_t row0 = (__shfl_sync(FULL, pdv, 0) & 0xFFFF) * nodes_u;       // all lanes take part in the shuffle
+                        if (small && e != ROLL_DEAD) cnext = cost[row0 + (e >> 16)];
                     }
                     if (lane == 0) t_look += (unsigned)live;
                     if (small) {
