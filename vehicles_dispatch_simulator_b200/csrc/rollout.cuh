@@ -785,7 +785,7 @@ rollout_local_kernel(DevParams P, int k0, int nticks, RollPolicy pol)
                 uint32_t mask = 0;
                 if (v0 < Vp) {
 #pragma unroll 1
-                    for (int j = 0; j < 16; j++) {
+                    for (int j = 0; j < 16 && v0 + j < P.V; j++) {   // (Vp is a multiple of 8, not of 16: stay inside)
                         const int v = v0 + j;
                         if (arrive[v] == IDLE16) {
                             const Philox x = philox4x32_10((uint32_t)v, (3u << 16) | (uint32_t)k, (uint32_t)g, (uint32_t)(g >> 32),
