@@ -595,6 +595,7 @@ rollout_local_kernel(DevParams P, int k0, int nticks, RollPolicy pol)
                 if (small && e != ROLL_DEAD) cnext = cost[(pdv0 & 0xFFFF) * nodes_u + (e >> 16)];
                 for (int j = 0; j < steps && live > 0; j++) {
                     if ((j & 31) == 0 && j > 0) {                        // next 32 orders of the cluster
+                        __syncwarp();
                         flush();
                         pdv = 0; idxv = 0;
                         if (j + lane < steps) { pdv = spd_t[b0 + j + lane]; idxv = sidx_t[b0 + j + lane]; }
@@ -654,6 +655,7 @@ rollout_local_kernel(DevParams P, int k0, int nticks, RollPolicy pol)
                     }
                     live--;
                 }
+                __syncwarp();            // the lanes' reads of key[] / icnt[c] above are ordered before the writes below
                 flush();
                 if (lane == 0) icnt[c] = (uint32_t)live;                     // len(IdleVehicles) after the match phase
             }
