@@ -98,3 +98,31 @@ def test_fused_policy_rollout_equals_per_tick(cuda_device, V, prob, windows):
     n = len(minute) - 1
     assert np.array_equal(a.tensors["order_res"][:, :n].cpu().numpy(), b.tensors["order_res"][:, :n].cpu().numpy())
     a.close(); b.close()
+
+
+def test_policy_rollout_with_neighbour_search_runs_per_tick(cuda_device):
+    """with NeighborCanServer the hook cannot be fused (orders of a replica are sequential across clusters):
+    rollout_policy_random runs the per-tick launches itself and gives the same state as the explicit loop."""
+    from vehicles_dispatch_simulator_b200.engine import DispatchEngine, tick_offsets
+    from vehicles_dispatch_simulator_b200.synthetic import synthetic_grid_city
+    rng = np.random.default_rng(5)
+    city = synthetic_grid_city(side_m=800, service_m=1600, neighbor_can_server=True, n_nodes=500)
+    V, R = 300, 2
+    minute, pick, drop = random_orders(city, 3000, rng)
+    off, T = tick_offsets(minute, 10)
+    loc0 = rng.choice(city.valid_nodes(), (R, V)).astype(np.int32)
+    engines = []
+    for _ in range(2):
+        e = DispatchEngine(city, V, replicas=R, ticks=T, max_orders=len(minute), max_orders_per_tick=int(np.diff(off).max()))
+        e.bind_shared_orders(minute, pick, drop)
+        e.reset(loc0)
+        engines.append(e)
+    a, b = engines
+    for k in range(T):
+        a.tick(k)
+        a.policy_random_dispatch(k, seed=3, first_replica=0, prob=0.2)
+    b.rollout_policy_random(0, T, seed=3, first_replica=0, prob=0.2)
+    assert np.array_equal(a.stats().cpu().numpy(), b.stats().cpu().numpy())
+    for name in ("veh_loc", "veh_cluster", "veh_arrive", "veh_dest", "veh_key", "idle_live"):
+        assert np.array_equal(a.tensors[name].cpu().numpy(), b.tensors[name].cpu().numpy()), name
+    a.close(); b.close()

@@ -318,8 +318,13 @@ class DispatchEngine:
     def rollout_policy_random(self, tick0=0, nticks=None, seed=1234, first_replica=0, prob=0.05):
         """Ticks [tick0, tick0+nticks) with the device-resident random DispatchFunction hook after every tick,
         FUSED into the replica-resident rollout kernel: one launch, bit-identical to
-        `for k: tick(k); policy_random_dispatch(k, ...)`.  Depth-0 engines only (VdsError otherwise)."""
+        `for k: tick(k); policy_random_dispatch(k, ...)`.  Engines with neighbour search run exactly that loop."""
         nticks = self.T - tick0 if nticks is None else nticks
+        if not self.fused or (self.city.neighbor_can_server and self.city.depth_limit > 0):
+            for k in range(int(tick0), int(tick0) + int(nticks)):      # neighbour search: same hook, per-tick launches
+                self.tick(k)
+                self.policy_random_dispatch(k, seed=seed, first_replica=first_replica, prob=prob)
+            return
         p = self._policy_tables()
         q32 = min(0xFFFFFFFF, int(prob * 4294967296.0))
         self._ck(self.L.vds_rollout_policy_random(self.h, int(tick0), int(nticks), C.c_uint64(seed), C.c_int64(first_replica),
