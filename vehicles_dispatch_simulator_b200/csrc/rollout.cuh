@@ -97,17 +97,15 @@ __device__ __forceinline__ void block_scan_u32(const uint32_t *cnt, uint32_t *of
     for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += t; }
     if (lane == 31) wtot[w] = incl;
     __syncthreads();
-    if (w == 0) {
-        uint32_t t = lane < NW ? wtot[lane] : 0, ti = t;
+    // every warp scans the (<= 32) warp totals itself: one barrier less than electing warp 0
+    const uint32_t t = lane < NW ? wtot[lane] : 0;
+    uint32_t ti = t;
 #pragma unroll
-        for (int d = 1; d < NW; d <<= 1) { uint32_t u = __shfl_up_sync(FULL, ti, d); if (lane >= d) ti += u; }
-        if (lane < NW) wtot[lane] = ti - t;
-        if (lane == NW - 1) wtot[NW] = ti;
-    }
-    __syncthreads();
-    uint32_t run = wtot[w] + incl - s;
+    for (int d = 1; d < NW; d <<= 1) { uint32_t u = __shfl_up_sync(FULL, ti, d); if (lane >= d) ti += u; }
+    const uint32_t wbase = __shfl_sync(FULL, ti - t, w), total = __shfl_sync(FULL, ti, NW - 1);
+    uint32_t run = wbase + incl - s;
     for (int i = 0; i < ipt; i++) if (b + i < C) { uint32_t c = cnt[b + i]; off[b + i] = run; run += c; }
-    if (tid == 0) off[C] = wtot[NW];
+    if (tid == 0) off[C] = total;
     __syncthreads();
 }
 
@@ -298,6 +296,7 @@ rollout_local_kernel(DevParams P, int k0, int nticks, RollPolicy pol)
     uint16_t *wl = reinterpret_cast<uint16_t *>(smraw + L.wl);
     uint16_t *wl_ix = reinterpret_cast<uint16_t *>(smraw + L.wl_ix);
     uint16_t *wla = reinterpret_cast<uint16_t *>(smraw + L.wla);
+    uint32_t *arr_cnt = reinterpret_cast<uint32_t *>(acc + 7);           // arrival-queue length (acc[0..6] are the window sums)
 
     const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const size_t vb = (size_t)r * Vp;
@@ -393,9 +392,8 @@ rollout_local_kernel(DevParams P, int k0, int nticks, RollPolicy pol)
             // later ticks: only ARRIVALS change the counts.  The packed scan just queues the arriving vehicles
             // (the idle-slot pool is free until phase 4 and serves as the queue); they are then handled densely,
             // one thread each, instead of through eight predicated per-slot blocks per thread.
-            if (tid == 0) wl_cnt[3] = 0;
+            // (the arrival counter arr_cnt was reset in phase 5 of the previous tick, three barriers ago)
             RPROF(11)
-            __syncthreads();
             RPROF(12)
             // two u16 per 32-bit op: (0x8000 + k) - (t & 0x7FFF) keeps bit 15 iff (t & 0x7FFF) <= k, and never borrows
             // into the neighbouring half; idle (0xFFFF) and padding (0x7FFF) entries have 0x7FFF > k.
@@ -410,14 +408,14 @@ rollout_local_kernel(DevParams P, int k0, int nticks, RollPolicy pol)
                     while (b) {
                         const int p = __ffs(b) - 1; b &= b - 1;
                         const int j = p < 16 ? 2 * p : 2 * (p - 16) + 1;
-                        ent[atomicAdd(&wl_cnt[3], 1u)] = (uint32_t)(g * 8 + j);
+                        ent[atomicAdd(arr_cnt, 1u)] = (uint32_t)(g * 8 + j);
                     }
                 }
             }
             RPROF(13)
             __syncthreads();
             RPROF(14)
-            const int n_arr = (int)wl_cnt[3];
+            const int n_arr = (int)*arr_cnt;
             for (int i = tid; i < n_arr; i += THREADS) {
                 const int v = (int)ent[i];
                 const uint32_t kk = key[v];
@@ -476,6 +474,7 @@ rollout_local_kernel(DevParams P, int k0, int nticks, RollPolicy pol)
             const int tail0 = head + 4 * n4;
             if (tail0 + tid < n_tick) p[tail0 + tid] = 0x0000FFFFu;
             if (tid < 4) wl_cnt[tid] = 0;
+            if (tid == 4) *arr_cnt = 0;                                  // next tick's arrival queue
         }
         RPROF(3)
         __syncthreads();
