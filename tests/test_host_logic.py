@@ -195,3 +195,16 @@ def test_demand_tables_shape():
     assert (np.diff(t.zipf_cdf.astype(np.int64)) >= 0).all()
     p = np.diff(np.concatenate([[0], t.zipf_cdf.astype(np.float64)])) / 2 ** 32
     assert p[0] > 5 * p[99]                               # heavy head (exponent 0.83)
+
+
+def test_bench_stdout_carries_only_the_json_line():
+    """bench.py points fd 1 at stderr for the whole run (NCCL prints its version banner to stdout behind Python's
+    back) and writes the one JSON line to a private duplicate of the original stdout."""
+    import subprocess
+    import sys
+    code = ("import sys, os; sys.path.insert(0, %r); import bench; bench._stdout_only_for_the_json_line(); "
+            "os.write(1, b'library noise\\n'); print('python noise'); bench.emit_json({'ok': 1})" % ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == '{"ok": 1}\n'
+    assert "library noise" in r.stderr and "python noise" in r.stderr
