@@ -220,7 +220,9 @@ int  vds_rollout_policy_random(vds_handle h, int tick0, int nticks, uint64_t see
  * With prepared orders this is ONE launch of the replica-resident rollout
  * kernel (a replica's vehicle state lives in shared memory for all nticks);
  * the per-cluster outputs (per_match ... n_orders) then hold the LAST tick's
- * values, exactly what the per-phase calls would leave behind. */
+ * values, exactly what the per-phase calls would leave behind.  SupplyExpect is
+ * an output nothing on the path reads, so either form computes it once, after
+ * the last tick of the window. */
 int  vds_rollout(vds_handle h, int tick0, int nticks, void *stream);
 
 /* One fused tick == vds_rollout(h, tick, 1, stream): the call an RL loop makes

@@ -554,7 +554,7 @@ match_search_kernel(DevParams P, int k, int staged, int n_sidx, int n_ridx)
 // SupplyExpectFunction (simulator.py:880-891): vehicles in cluster c's arrival
 // table that carry an order and arrive by the start of the next slot.
 __global__ void __launch_bounds__(UPD_THREADS)
-supply_kernel(DevParams P, int k)
+supply_kernel(DevParams P, int k, int ticks_add)
 {
     extern __shared__ int sm[];
     const int r = blockIdx.x, tid = threadIdx.x, C = P.C;
@@ -580,7 +580,7 @@ supply_kernel(DevParams P, int k)
     __syncthreads();
     int *g_s = P.supply + (size_t)r * C;
     for (int i = tid; i < C; i += UPD_THREADS) g_s[i] = sm[i];
-    if (tid == 0) P.stats[(size_t)r * VDS_NUM_STATS + VDS_STAT_TICKS] += 1;
+    if (tid == 0) P.stats[(size_t)r * VDS_NUM_STATS + VDS_STAT_TICKS] += ticks_add;
 }
 
 // ----------------------------------------------------------------- dispatch
@@ -1047,7 +1047,7 @@ int vds_match(vds_handle h, int tick, void *stream)
 int vds_supply_expect(vds_handle h, int tick, void *stream)
 {
     int rc = ready(h, false); if (rc) return rc;
-    supply_kernel<<<h->P.R, UPD_THREADS, sizeof(int) * h->P.C, (cudaStream_t)stream>>>(h->P, tick);
+    supply_kernel<<<h->P.R, UPD_THREADS, sizeof(int) * h->P.C, (cudaStream_t)stream>>>(h->P, tick, 1);
     CKL("supply_kernel");
     return VDS_OK;
 }
@@ -1123,8 +1123,11 @@ int vds_rollout(vds_handle h, int tick0, int nticks, void *stream)
     for (int k = tick0; k < tick0 + nticks; k++) {
         if ((rc = vds_update(h, k, stream))) return rc;
         if ((rc = vds_match(h, k, stream))) return rc;
-        if ((rc = vds_supply_expect(h, k, stream))) return rc;
     }
+    // SupplyExpect is an output, nothing on the path reads it: like the fused kernel, a hook-free window computes
+    // it only where it is observable -- after its last tick (and books the whole window's tick count there)
+    supply_kernel<<<h->P.R, UPD_THREADS, sizeof(int) * h->P.C, (cudaStream_t)stream>>>(h->P, tick0 + nticks - 1, nticks);
+    CKL("supply_kernel");
     return VDS_OK;
 }
 
