@@ -368,15 +368,16 @@ match_local_kernel(DevParams P, int k)
 // The search lists and their inverses (read on every order's dependent chain) are staged in shared memory
 // once per CTA when they fit (`staged`; sizes from vds_bind_static).
 #define MS_WARPS 7          // 7 warps x 4 CTAs = 28 warps/SM: 4096 replicas are one wave on 148 SMs at 72 registers, no spills
+template <bool STAGED>          // compile-time, so the table reads become LDS (not generic LD) in the staged build
 __global__ void __launch_bounds__(MS_WARPS * 32, 4)
-match_search_kernel(DevParams P, int k, int staged, int n_sidx, int n_ridx)
+match_search_kernel(DevParams P, int k, int n_sidx, int n_ridx)
 {
     extern __shared__ int sm[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int C = P.C;
     const int *soff = P.soff, *roff = P.roff; const uint16_t *sidx = P.sidx, *ridx = P.ridx;
     int tab_ints = 0;
-    if (staged) {
+    if constexpr (STAGED) {
         int *soff_s = sm, *roff_s = sm + (C + 1);
         uint16_t *sidx_s = reinterpret_cast<uint16_t *>(sm + 2 * (C + 1));
         uint16_t *ridx_s = sidx_s + ((n_sidx + 1) & ~1);
@@ -874,7 +875,8 @@ int vds_create(const vds_config *cfg, vds_handle *out)
     const int prep_smem = (int)sizeof(int) * (2 * Cp + 4 + 16 + PREP_WARPS * Cp);
     CK(cudaFuncSetAttribute(prepare_orders_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, prep_smem));
     { const char *e = getenv("VDS_FUSED_SEARCH"); h->fused_search = e && e[0] == '1'; }
-    CK(cudaFuncSetAttribute(match_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaFuncSetAttribute(match_search_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaFuncSetAttribute(match_search_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     // replica-resident rollout kernel: pick the CTA width from how many replicas fit one SM
     P.L = roll_layout(P.Vp, P.C);
     h->roll_smem = P.L.total;
@@ -1037,8 +1039,10 @@ int vds_match(vds_handle h, int tick, void *stream)
         const int tab = 2 * (P.C + 1) + ((h->n_sidx + 1) >> 1) + ((h->n_ridx + 1) >> 1);
         const int staged = h->n_sidx >= 0 && (size_t)(tab + per_cta) * sizeof(int) <= 64 * 1024;
         const int smem = (int)sizeof(int) * ((staged ? tab : 0) + per_cta);
-        match_search_kernel<<<(P.R + MS_WARPS - 1) / MS_WARPS, MS_WARPS * 32, smem, (cudaStream_t)stream>>>(
-            P, tick, staged, h->n_sidx, h->n_ridx);
+        if (staged) match_search_kernel<true><<<(P.R + MS_WARPS - 1) / MS_WARPS, MS_WARPS * 32, smem, (cudaStream_t)stream>>>(
+                        P, tick, h->n_sidx, h->n_ridx);
+        else match_search_kernel<false><<<(P.R + MS_WARPS - 1) / MS_WARPS, MS_WARPS * 32, smem, (cudaStream_t)stream>>>(
+                        P, tick, h->n_sidx, h->n_ridx);
         CKL("match_search_kernel");
     }
     return VDS_OK;
