@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define VDS_ABI_VERSION 3
+#define VDS_ABI_VERSION 4
 
 typedef enum vds_status {
     VDS_OK = 0,
@@ -189,7 +189,10 @@ int  vds_supply_expect(vds_handle h, int tick, void *stream);
 /* The implied dispatch primitive for tick k.  CSR over replicas:
  * replica r applies moves [move_off[r], move_off[r+1]) in array order; each is
  * (vehicle index, destination node).  A move whose vehicle is not idle is
- * skipped.  Device pointers. */
+ * skipped; when several moves of one replica name the same vehicle the LOWEST
+ * move index wins (what a sequential loop over the array does) -- deterministic.
+ * Only applied moves are numbered (the dispatch sequence in veh_key).  Uses the
+ * replica's idle_ent scratch (dead after the match phase).  Device pointers. */
 int  vds_dispatch(vds_handle h, int tick, const int32_t *move_off, const int32_t *move_veh,
                   const int32_t *move_node, int total_moves, void *stream);
 
@@ -233,9 +236,45 @@ int  vds_tick(vds_handle h, int tick, void *stream);
 int  vds_rollout_is_fused(vds_handle h);
 /* CTA width of that kernel (0 if a replica does not fit one SM's shared memory). */
 int  vds_rollout_threads(vds_handle h);
+/* name of the kernel vds_rollout launches for this handle (for profiles / bench.py's roofline line) */
+const char *vds_rollout_kernel_name(vds_handle h);
 
 /* out[R][VDS_NUM_STATS] (device): finalises SumOrderValue (simulator.py:1095-1100). */
 int  vds_stats(vds_handle h, int64_t *out, void *stream);
+
+/* ---- observation ring (the state tensor an RL agent reads every tick) --------------------
+ * obs: u16 [R][ring][4][C], slot (tick mod ring), fields
+ *   0 idle vehicles before the match  (Cluster.PerMatchIdleVehicles,    simulator.py:909-910)
+ *   1 demand                          (len(Cluster.Orders),             simulator.py:918, 973)
+ *   2 SupplyExpect                    (simulator.py:880-891)
+ *   3 idle vehicles after the match   (Cluster.PerDispatchIdleVehicles, simulator.py:1080-1081)
+ * Once bound (obs != NULL), vds_rollout / vds_tick / vds_rollout_policy_random write every tick's record
+ * themselves (the replica-resident kernel has all four in shared memory); vds_observe packs it after the
+ * per-phase calls update -> match -> supply_expect of one tick.  obs == NULL unbinds. */
+int  vds_bind_observations(vds_handle h, uint16_t *obs, int ring);
+int  vds_observe(vds_handle h, int tick, void *stream);
+
+/* GetTimeAndWeather (simulator.py:842-866) evaluated at the start time of every tick:
+ * out f32 [T][10] = day, weekday, weekend, hour, minute, WeatherType, MinimumTemperature, MaximumTemperature,
+ * WindDirection, WindPower.  t0_minutes: wall-clock minutes since 1970-01-01 of tick 0 (RealExpTime at step 0);
+ * the five tables are the reference's normalised Nov-2016 arrays (60 half-days, 30 days each), device
+ * pointers.  Rows outside November are NaN (the reference raises there). */
+int  vds_time_features(vds_handle h, int64_t t0_minutes, const float *weather60, const float *tmin30, const float *tmax30,
+                       const float *wdir30, const float *wpow30, float *out, void *stream);
+
+/* Reload / FocusOnLocalRegion as a device-side stream swap + compaction (simulator.py:130-212, 325-339,
+ * 356-370): replaces the bound SHARED order stream by the n orders (minute since the first
+ * order's release, pickup node, delivery node; device pointers, sorted by minute).  drop_uncovered != 0
+ * removes every order whose pickup or delivery node lies outside all clusters (IsOrderInLimitRegion) keeping
+ * the relative order of the rest.  Writes order_pd, tick_off and n_orders[0] (the kept count); the caller
+ * then runs vds_prepare_orders(h, n_orders, stream).  Needs order_replicas == 1 and the derived arrays. */
+int  vds_load_orders(vds_handle h, const int32_t *minute, const int32_t *pickup, const int32_t *delivery, int n,
+                     int drop_uncovered, int32_t *n_orders, void *stream);
+
+/* Cluster-mode graph builder (simulator.py:594-631): out[i][j] (int64 [C][C]) = sum of
+ * RoadCost(k, l) over k in Nodes(i), l in Nodes(j) from the bound cost table; Cluster.Nodes as CSR
+ * (cl_node_off i32[C+1], cl_nodes u16).  The host divides by |i||j| and applies the neighbour rule. */
+int  vds_cluster_cost_sums(vds_handle h, const int32_t *cl_node_off, const uint16_t *cl_nodes, int64_t *out, void *stream);
 
 int  vds_sync(vds_handle h, void *stream);
 

@@ -99,7 +99,7 @@ def run_reference(workdir, ClusterMode="Grid", VehiclesNumber=6000,
                   SideLengthMeter=800, VehiclesServiceMeter=800,
                   NeighborCanServer=False, seed=0,
                   LocalRegionBound=(104.011, 104.125, 30.618, 30.703),
-                  dispatch=False, record_idle_lists=True, order_date="1101"):
+                  dispatch=False, record_idle_lists=True, order_date="1101", FocusOnLocalRegion=False):
     """Returns (inputs dict, traces dict) of numpy arrays."""
     _ensure_stub_and_copy()
     os.environ["TZ"] = "UTC"
@@ -172,7 +172,7 @@ def run_reference(workdir, ClusterMode="Grid", VehiclesNumber=6000,
                      TimePeriods=setting.TIMESTEP, LocalRegionBound=LocalRegionBound,
                      SideLengthMeter=SideLengthMeter,
                      VehiclesServiceMeter=VehiclesServiceMeter,
-                     NeighborCanServer=NeighborCanServer, FocusOnLocalRegion=False)
+                     NeighborCanServer=NeighborCanServer, FocusOnLocalRegion=FocusOnLocalRegion)
         sim.CreateAllInstantiate(order_date)
         sim._vidx = {id(v): i for i, v in enumerate(sim.Vehicles)}
 

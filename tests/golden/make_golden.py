@@ -3,6 +3,7 @@
 
     python tests/golden/make_golden.py            # small city (committed)
     python tests/golden/make_golden.py --real     # + shipped-data traces (git-ignored, travels with gpurun)
+    python tests/golden/make_golden.py --real --only grid400v10000   # (re)generate one real case, keep the others
 
 Small city: a 420-node synthetic dataset written in the reference's own CSV
 formats under tests/golden/small_city/data/ (committed, ~1.5 MB), run through
@@ -32,11 +33,18 @@ SMALL = {
     "kmeans_d1": dict(ClusterMode="KmeansClustering", VehiclesNumber=100, VehiclesServiceMeter=1200, NeighborCanServer=True),
     "grid_d0_dispatch": dict(ClusterMode="Grid", VehiclesNumber=150, dispatch=True),
     "grid_d1_dispatch": dict(ClusterMode="Grid", VehiclesNumber=150, VehiclesServiceMeter=1600, NeighborCanServer=True, dispatch=True),
+    # FocusOnLocalRegion (simulator.py:356-370, 382-402): nodes and orders outside the reference's own sub-box
+    # (config/setting.py:16) are dropped, the grid is laid over the sub-box (10 x 10 cells of 800 m)
+    "grid_d1_focus": dict(ClusterMode="Grid", VehiclesNumber=120, VehiclesServiceMeter=1600, NeighborCanServer=True,
+                          FocusOnLocalRegion=True, LocalRegionBound=(104.035, 104.105, 30.625, 30.695)),
 }
 REAL = {
     "kmeans": dict(ClusterMode="KmeansClustering", VehiclesNumber=2000),
     "grid6000": dict(ClusterMode="Grid", VehiclesNumber=6000),
     "grid5000d3": dict(ClusterMode="Grid", VehiclesNumber=5000, VehiclesServiceMeter=2800, NeighborCanServer=True),
+    # SURVEY 8d "parity variant of the 768-grid" (BASELINE config 5's shape on the REAL city): 32 x 24 cells of
+    # 400 m, 111 of them empty, V = 10000
+    "grid400v10000": dict(ClusterMode="Grid", VehiclesNumber=10000, SideLengthMeter=400, VehiclesServiceMeter=400),
 }
 
 
@@ -109,20 +117,28 @@ def digest(tr):
 
 
 def main():
+    only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None
     small_dir = os.path.join(HERE, "small_city")
-    write_small_city(os.path.join(small_dir, "data"))
-    nb = os.path.join(small_dir, "data", BOUND_STR + "192KmeansClusteringNeighbor.csv")
-    if os.path.exists(nb):
-        os.remove(nb)                                    # let the reference compute it
-    for name, kw in SMALL.items():
-        inp, tr, _ = H.run_reference(small_dir, seed=0, **kw)
-        save(os.path.join(HERE, f"small_{name}.npz"), inp, tr)
-        print("small", name, tr["final"].tolist())
+    if only is None:
+        if "--small-only" not in sys.argv:
+            write_small_city(os.path.join(small_dir, "data"))
+            nb = os.path.join(small_dir, "data", BOUND_STR + "192KmeansClusteringNeighbor.csv")
+            if os.path.exists(nb):
+                os.remove(nb)                                    # let the reference compute it
+        for name, kw in SMALL.items():
+            if "--small-only" in sys.argv and name != sys.argv[sys.argv.index("--small-only") + 1]:
+                continue
+            inp, tr, _ = H.run_reference(small_dir, seed=0, **kw)
+            save(os.path.join(HERE, f"small_{name}.npz"), inp, tr)
+            print("small", name, tr["final"].tolist())
     if "--real" in sys.argv:
         wd = H.real_data_dir()
         os.makedirs(os.path.join(HERE, "_real"), exist_ok=True)
-        dg = {}
+        dpath = os.path.join(HERE, "real_digest.json")
+        dg = json.load(open(dpath)) if (only and os.path.exists(dpath)) else {}
         for name, kw in REAL.items():
+            if only and name != only:
+                continue
             cache = f"/tmp/vds_ref/real_{name}.npz"
             if os.path.exists(cache):
                 z = np.load(cache)
@@ -130,12 +146,12 @@ def main():
                 tr = {k[3:]: z[k] for k in z.files if k.startswith("tr_")}
             else:
                 inp, tr, _ = H.run_reference(wd, seed=0, **kw)
-            cost = inp.pop("cost_u8")                    # identical for the three configs: stored once
+            cost = inp.pop("cost_u8")                    # identical for all real configs: stored once
             np.savez_compressed(os.path.join(HERE, "_real", "real_cost.npz"), cost_u8=cost)
             save(os.path.join(HERE, "_real", f"real_{name}.npz"), inp, tr)
             dg[name] = digest(tr)
             print("real", name, dg[name]["final"])
-        json.dump(dg, open(os.path.join(HERE, "real_digest.json"), "w"), indent=1)
+        json.dump(dg, open(dpath, "w"), indent=1)
 
 
 if __name__ == "__main__":

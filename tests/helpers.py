@@ -177,8 +177,8 @@ def engine_replica_orders(eng, r, n_slots):
 import os as _os
 
 GOLDEN = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden")
-SMALL_CASES = ("grid_d0", "grid_d2", "kmeans_d1", "grid_d0_dispatch", "grid_d1_dispatch")
-REAL_CASES = ("kmeans", "grid6000", "grid5000d3")
+SMALL_CASES = ("grid_d0", "grid_d2", "kmeans_d1", "grid_d0_dispatch", "grid_d1_dispatch", "grid_d1_focus")
+REAL_CASES = ("kmeans", "grid6000", "grid5000d3", "grid400v10000")
 
 
 def load_golden(name, real=False):

@@ -212,9 +212,10 @@ def test_fused_rollout_golden(cuda_device, name):
     assert tuple(st[0][:6]) == tuple(z["tr_final"][:6])
 
 
-@pytest.mark.parametrize("case", ["kmeans", "grid5000d3"])
+@pytest.mark.parametrize("case", ["kmeans", "grid6000", "grid5000d3", "grid400v10000"])
 def test_fused_rollout_real_day(cuda_device, case):
-    """Shipped 2016-11-01 day (Kmeans-192 / 2000 vehicles = BASELINE configs[0]; Grid / 5000 / depth 3) if present."""
+    """Shipped 2016-11-01 day (Kmeans-192 / 2000 vehicles = BASELINE configs[0]; Grid / 6000; Grid / 5000 / depth 3;
+    Grid SideLengthMeter=400 / 10000 vehicles = the real-city parity variant of configs[4]) if present."""
     z = load_golden(case, real=True)
     if z is None:
         pytest.skip("tests/golden/_real not present (generated by make_golden.py --real)")

@@ -23,6 +23,8 @@ GOLDEN_FINAL = {   # SURVEY.md 8c / BASELINE.md table
     "kmeans": (209422, 141716, 102637, 1671284),
     "grid6000": (209422, 72496, 145514, 3375797),
     "grid5000d3": (209422, 46916, 405749, 4003693),
+    # SURVEY 8d's parity variant of BASELINE config 5: real city, Grid, SideLengthMeter=400 (32 x 24 cells, 111 empty), V=10000
+    "grid400v10000": (209422, 81169, 55940, 3167227),
 }
 
 

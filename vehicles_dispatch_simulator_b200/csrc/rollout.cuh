@@ -341,7 +341,7 @@ rollout_local_kernel(DevParams P, int k0, int nticks, RollPolicy pol)
     RPROF_DECL
 
     for (int k = k0; k < k0 + nticks; k++) {
-        const bool emit = (k == k0 + nticks - 1) || P.trace != nullptr;
+        const bool emit = (k == k0 + nticks - 1) || P.trace != nullptr || P.obs != nullptr;
         const int tb = toff[k], n_tick = toff[k + 1] - tb;
         const uint16_t *coff = P.coff + ((size_t)ro * P.T + k) * (C + 1);
         // this tick's per-cluster order offsets: issue the loads now, park them in smem after phase 2
@@ -443,6 +443,10 @@ rollout_local_kernel(DevParams P, int k0, int nticks, RollPolicy pol)
             if (P.trace) {
                 int *tr = P.trace + (((size_t)r * P.T + k) * 4) * C;
                 for (int i = tid; i < C; i += THREADS) { tr[i] = (int)icnt[i]; tr[3 * C + i] = (int)ooff[i + 1] - (int)ooff[i]; }
+            }
+            if (P.obs) {                                                 // observation ring: idle before match, demand
+                uint16_t *ob = P.obs + ((size_t)r * P.obs_ring + (k % P.obs_ring)) * 4 * C;
+                for (int i = tid; i < C; i += THREADS) { ob[i] = (uint16_t)icnt[i]; ob[C + i] = (uint16_t)(ooff[i + 1] - ooff[i]); }
             }
         }
 
@@ -769,6 +773,10 @@ rollout_local_kernel(DevParams P, int k0, int nticks, RollPolicy pol)
             __syncthreads();
             int *g_s = P.supply + (size_t)r * C;
             for (int i = tid; i < C; i += THREADS) { g_s[i] = (int)ioff[i]; if (tr) tr[2 * C + i] = (int)ioff[i]; }
+            if (P.obs) {                                                 // observation ring: SupplyExpect, idle after match
+                uint16_t *ob = P.obs + ((size_t)r * P.obs_ring + (k % P.obs_ring)) * 4 * C;
+                for (int i = tid; i < C; i += THREADS) { ob[2 * C + i] = (uint16_t)ioff[i]; ob[3 * C + i] = (uint16_t)icnt[i]; }
+            }
             __syncthreads();
         }
 

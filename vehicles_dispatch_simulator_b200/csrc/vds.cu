@@ -53,6 +53,7 @@ struct DevParams {
     long long *stats; uint2 *idle_ent; int *idle_off, *bucket_off; uint16_t *bucket_ord; int *disp_seq;
     // derived order layout (vds_prepare_orders) + optional rollout trace
     const uint32_t *spd; const uint16_t *sord; const uint16_t *coff; const long long *tick_value; int *trace;
+    uint16_t *obs; int obs_ring;             // optional observation ring (vds_bind_observations): [R][ring][4][C] u16
     RollLayout L;
 };
 
@@ -586,39 +587,68 @@ supply_kernel(DevParams P, int k, int ticks_add)
 
 // ----------------------------------------------------------------- dispatch
 // The implied dispatch primitive (reference touch points
-// simulator.py:805-808, 889, 1018, 1117-1119).
-__global__ void __launch_bounds__(128)
+// simulator.py:805-808, 889, 1018, 1117-1119).  Moves of one replica are applied "in array order": a move whose
+// vehicle is not idle is skipped, and when several moves name the same vehicle the LOWEST move index wins
+// (the later ones find the vehicle en route -- exactly what a sequential loop over the array does).  Only
+// applied moves are numbered (dispatch sequence = insertion order of the reference's VehiclesArrivetime dicts).
+//   pass 1: claim[v] = min(move index) per named vehicle (idle_ent is free scratch after the match phase)
+//   pass 2: move i applies iff it holds the claim and the vehicle is idle; block scan numbers the applied moves
+#define DISP_THREADS 128
+__global__ void __launch_bounds__(DISP_THREADS)
 dispatch_kernel(DevParams P, int k, const int *move_off, const int *move_veh, const int *move_node, int stride)
 {
-    __shared__ int s_n; __shared__ long long s_cost;
-    const int r = blockIdx.x, tid = threadIdx.x;
-    if (tid == 0) { s_n = 0; s_cost = 0; }
-    __syncthreads();
+    __shared__ int s_n; __shared__ long long s_cost; __shared__ int s_w[DISP_THREADS / 32]; __shared__ int s_run;
+    const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid == 0) { s_n = 0; s_cost = 0; s_run = 0; }
     // stride == 0: CSR over replicas (move_off[R+1]); stride > 0: move_off[r] = COUNT, lists at r * stride
     const int m0 = stride ? r * stride : move_off[r], m = stride ? move_off[r] : move_off[r + 1] - m0;
     const size_t vb = (size_t)r * P.Vp;
-    const int dseq = P.disp_seq[r];
-    for (int i = tid; i < m; i += blockDim.x) {
-        const int v = move_veh[m0 + i], node = move_node[m0 + i];
-        if (v < 0 || v >= P.V || node < 0 || node >= P.nodes) continue;
-        const int tc = P.n2c[node];
-        if (tc == 0xFFFF) continue;
-        const int loc = P.veh_loc[vb + v];
-        const int cost = P.cost[(size_t)node * P.nodes + loc];        // RoadCost(loc, node)
-        int d = (cost + P.period - 1) / P.period; if (d < 1) d = 1;
-        const unsigned short old = atomicCAS((unsigned short *)(P.veh_arrive + vb + v), (unsigned short)IDLE16,
-                                             (unsigned short)(k + d));      // no order on board
-        if (old != IDLE16) continue;                                    // not idle: skip
-        const int src = P.veh_cluster[vb + v];
-        P.veh_dest[vb + v] = (uint16_t)node;
-        P.veh_cluster[vb + v] = (uint16_t)tc;
-        P.veh_key[vb + v] = ((uint32_t)k << 21) | (uint32_t)(16384 + ((dseq + i) & 16383));
-        atomicSub(&P.idle_live[(size_t)r * P.C + src], 1);
-        atomicAdd(&s_n, 1); atomicAdd((unsigned long long *)&s_cost, (unsigned long long)cost);
+    unsigned *claim = reinterpret_cast<unsigned *>(P.idle_ent + vb);      // [Vp] words of the replica's slot scratch
+    auto valid = [&](int v, int node) {
+        return v >= 0 && v < P.V && node >= 0 && node < P.nodes && P.n2c[node] != 0xFFFF;
+    };
+    for (int i = tid; i < m; i += DISP_THREADS) {
+        const int v = move_veh[m0 + i];
+        if (v >= 0 && v < P.V) claim[v] = 0xFFFFFFFFu;
     }
     __syncthreads();
+    for (int i = tid; i < m; i += DISP_THREADS) {
+        const int v = move_veh[m0 + i], node = move_node[m0 + i];
+        if (valid(v, node)) atomicMin(&claim[v], (unsigned)i);
+    }
+    __syncthreads();
+    const int dseq = P.disp_seq[r];
+    for (int base = 0; base < m; base += DISP_THREADS) {
+        const int i = base + tid;
+        int v = -1, node = 0; bool go = false;
+        if (i < m) {
+            v = move_veh[m0 + i]; node = move_node[m0 + i];
+            go = valid(v, node) && claim[v] == (unsigned)i && P.veh_arrive[vb + v] == IDLE16;   // not idle: skipped
+        }
+        const unsigned bal = __ballot_sync(FULL, go);
+        if (lane == 0) s_w[w] = __popc(bal);
+        __syncthreads();
+        int seq = s_run + __popc(bal & lanemask_lt());
+        for (int ww = 0; ww < w; ww++) seq += s_w[ww];
+        if (go) {
+            const int tc = P.n2c[node];
+            const int loc = P.veh_loc[vb + v];
+            const int cost = P.cost[(size_t)node * P.nodes + loc];        // RoadCost(loc, node)
+            int d = (cost + P.period - 1) / P.period; if (d < 1) d = 1;
+            const int src = P.veh_cluster[vb + v];
+            P.veh_arrive[vb + v] = (uint16_t)(k + d);                     // no order on board (bit 15 clear)
+            P.veh_dest[vb + v] = (uint16_t)node;
+            P.veh_cluster[vb + v] = (uint16_t)tc;
+            P.veh_key[vb + v] = ((uint32_t)k << 21) | (uint32_t)(16384 + ((dseq + seq) & 16383));
+            atomicSub(&P.idle_live[(size_t)r * P.C + src], 1);
+            atomicAdd(&s_n, 1); atomicAdd((unsigned long long *)&s_cost, (unsigned long long)cost);
+        }
+        __syncthreads();
+        if (tid == 0) { int t = 0; for (int ww = 0; ww < DISP_THREADS / 32; ww++) t += s_w[ww]; s_run += t; }
+        __syncthreads();
+    }
     if (tid == 0) {
-        P.disp_seq[r] = dseq + m;
+        P.disp_seq[r] = dseq + s_run;
         long long *st = P.stats + (size_t)r * VDS_NUM_STATS;
         st[VDS_STAT_DISPATCH_NUM] += s_n; st[VDS_STAT_DISPATCH_COST] += s_cost;
     }
@@ -812,6 +842,121 @@ policy_random_kernel(DevParams P, int k, uint64_t seed, long long first_replica,
         __syncthreads();
     }
     if (tid == 0) move_cnt[r] = s_base;
+}
+
+
+// ------------------------------------------------- observation ring
+// The per-cluster state an RL agent reads every tick -- idle vehicles before the match
+// (PerMatchIdleVehicles, simulator.py:909-910), demand len(Cluster.Orders) (:918, 973), SupplyExpect (:880-891)
+// and idle vehicles after the match (PerDispatchIdleVehicles, :1080-1081) -- as ONE compact u16 record per
+// (replica, tick, cluster), written into slot (tick mod ring) of a ring the learner reads.  The fused rollout
+// kernels write it themselves; this kernel packs it after the per-phase calls of one tick.
+__global__ void observe_kernel(DevParams P, int k)
+{
+    const int r = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= P.C) return;
+    const size_t i = (size_t)r * P.C + c;
+    uint16_t *o = P.obs + ((size_t)r * P.obs_ring + (k % P.obs_ring)) * 4 * P.C;
+    o[c] = (uint16_t)P.per_match[i]; o[P.C + c] = (uint16_t)P.n_orders[i];
+    o[2 * P.C + c] = (uint16_t)P.supply[i]; o[3 * P.C + c] = (uint16_t)P.per_dispatch[i];
+}
+
+// GetTimeAndWeather (simulator.py:842-866) for the start time of every tick: day, weekday, weekend, hour, minute,
+// WeatherType, Min/MaxTemperature, WindDirection, WindPower.  t0_min = minutes since 1970-01-01 of tick 0 (local
+// wall clock, as the reference's naive datetimes); weather tables are the reference's normalised Nov-2016 arrays
+// (60 half-days, 4 x 30 days).  month != 11 raises in the reference: the row is filled with NaN.
+__global__ void time_features_kernel(int T, long long t0_min, int period, const float *weather60, const float *tmin30,
+                                     const float *tmax30, const float *wdir30, const float *wpow30, float *out)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= T) return;
+    const long long m = t0_min + (long long)k * period;
+    long long days = m / 1440; int mod = (int)(m % 1440); if (mod < 0) { mod += 1440; days -= 1; }
+    // civil from days (proleptic Gregorian), days since 1970-01-01
+    long long z = days + 719468;
+    const long long era = (z >= 0 ? z : z - 146096) / 146097;
+    const unsigned doe = (unsigned)(z - era * 146097);
+    const unsigned yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
+    const unsigned doy = doe - (365 * yoe + yoe / 4 - yoe / 100);
+    const unsigned mp = (5 * doy + 2) / 153;
+    const int day = (int)(doy - (153 * mp + 2) / 5 + 1);
+    const int month = (int)(mp < 10 ? mp + 3 : mp - 9);
+    int wd = (int)((days + 3) % 7); if (wd < 0) wd += 7;          // Monday = 0 (1970-01-01 was a Thursday)
+    const int hour = mod / 60, minute = mod % 60;
+    float *o = out + (size_t)k * 10;
+    if (month != 11 || day > 30) { for (int i = 0; i < 10; i++) o[i] = __int_as_float(0x7FC00000); return; }
+    o[0] = (float)day; o[1] = (float)wd; o[2] = (wd == 5 || wd == 6) ? 1.f : 0.f; o[3] = (float)hour; o[4] = (float)minute;
+    o[5] = weather60[2 * (day - 1) + (hour < 12 ? 0 : 1)];
+    o[6] = tmin30[day - 1]; o[7] = tmax30[day - 1]; o[8] = wdir30[day - 1]; o[9] = wpow30[day - 1];
+}
+
+// ------------------------------------- order-stream load: region compaction + tick offsets
+// Reload / FocusOnLocalRegion (simulator.py:130-212, 325-339, 356-370): a new day's orders replace the bound
+// stream; with drop_uncovered, orders whose pickup or delivery node lies outside every cluster
+// (IsOrderInLimitRegion) are removed and the rest keep their relative order (IDs are re-numbered 0..n-1).
+// One CTA; stable compaction by ballot + block scan over 1024-order chunks.
+#define LOAD_THREADS 1024
+__global__ void __launch_bounds__(LOAD_THREADS)
+load_orders_kernel(DevParams P, const int *minute, const int *pickup, const int *delivery, int n, int drop,
+                   uint32_t *order_pd, int *minute_out, int *n_out)
+{
+    __shared__ int s_w[LOAD_THREADS / 32]; __shared__ int s_run;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid == 0) s_run = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += LOAD_THREADS) {
+        const int i = base + tid;
+        int p = 0, d = 0, mi = 0; bool keep = false;
+        if (i < n) {
+            p = pickup[i]; d = delivery[i]; mi = minute[i];
+            keep = p >= 0 && p < P.nodes && d >= 0 && d < P.nodes &&
+                   (!drop || (P.n2c[p] != 0xFFFF && P.n2c[d] != 0xFFFF));
+        }
+        const unsigned bal = __ballot_sync(FULL, keep);
+        if (lane == 0) s_w[w] = __popc(bal);
+        __syncthreads();
+        int pos = s_run + __popc(bal & lanemask_lt());
+        for (int ww = 0; ww < w; ww++) pos += s_w[ww];
+        if (keep && pos < P.Nmax) { order_pd[pos] = (uint32_t)p | ((uint32_t)d << 16); minute_out[pos] = mi; }
+        __syncthreads();
+        if (tid == 0) { int t = 0; for (int ww = 0; ww < LOAD_THREADS / 32; ww++) t += s_w[ww]; s_run += t; }
+        __syncthreads();
+    }
+    if (tid == 0) *n_out = s_run;
+}
+// tick(o) = floor(minute / period) + 1, tick 0 is empty, the last order is never consumed
+// (simulator.py:912-915, 1037-1048): tick_off[k] = min(#orders with tick < k, n - 1)
+__global__ void tick_offsets_kernel(DevParams P, const int *minute, const int *n_in, int *tick_off)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > P.T) return;
+    int n = *n_in; if (n > P.Nmax) n = P.Nmax;
+    // minutes count from the first KEPT order's release (RealExpTime_0 = Orders[0].ReleasTime - period, Q7)
+    const long long lim = (long long)(n > 0 ? minute[0] : 0) + (long long)(k - 1) * P.period;   // minute < lim: ticks < k
+    int lo = 0, hi = n;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if ((long long)minute[mid] < lim) lo = mid + 1; else hi = mid; }
+    tick_off[k] = k == 0 ? 0 : min(lo, n > 0 ? n - 1 : 0);
+}
+
+// ---------------------------------- cluster-mode graph builder: inter-cluster road cost
+// CreateCluster (simulator.py:594-631): for every ordered cluster pair (i, j) the SUM of RoadCost(k, l) over
+// k in Nodes(i), l in Nodes(j) (exact integer; the host divides by |i||j| and applies the 4-nearest / < 15 rule).
+// One warp per pair: lanes stride the |i| x |j| block of the cost table (cost[l][k]).
+__global__ void __launch_bounds__(256)
+cluster_cost_sum_kernel(DevParams P, const int *cl_off, const uint16_t *cl_nodes, long long *out)
+{
+    const int lane = threadIdx.x & 31;
+    const long long pair = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (pair >= (long long)P.C * P.C) return;
+    const int i = (int)(pair / P.C), j = (int)(pair % P.C);
+    const int i0 = cl_off[i], ni = cl_off[i + 1] - i0, j0 = cl_off[j], nj = cl_off[j + 1] - j0;
+    long long s = 0;
+    for (int q = lane; q < ni * nj; q += 32) {
+        const int k = cl_nodes[i0 + q % ni], l = cl_nodes[j0 + q / ni];
+        s += P.cost[(size_t)l * P.nodes + k];
+    }
+    for (int d = 16; d; d >>= 1) s += __shfl_xor_sync(FULL, s, d);
+    if (lane == 0) out[pair] = s;
 }
 
 // =========================================================== host-side C ABI
@@ -1063,7 +1208,7 @@ int vds_dispatch(vds_handle h, int tick, const int32_t *move_off, const int32_t 
     if (!move_off || (total_moves > 0 && (!move_veh || !move_node)))
         return fail(h, VDS_ERR_INVALID, "vds_dispatch: null pointer");
     if (total_moves <= 0) return VDS_OK;
-    dispatch_kernel<<<h->P.R, 128, 0, (cudaStream_t)stream>>>(h->P, tick, move_off, move_veh, move_node, 0);
+    dispatch_kernel<<<h->P.R, DISP_THREADS, 0, (cudaStream_t)stream>>>(h->P, tick, move_off, move_veh, move_node, 0);
     CKL("dispatch_kernel");
     return VDS_OK;
 }
@@ -1074,7 +1219,7 @@ int vds_dispatch_strided(vds_handle h, int tick, const int32_t *move_cnt, const 
     int rc = ready(h, false); if (rc) return rc;
     if (!move_cnt || !move_veh || !move_node || stride < 1)
         return fail(h, VDS_ERR_INVALID, "vds_dispatch_strided: bad arguments");
-    dispatch_kernel<<<h->P.R, 128, 0, (cudaStream_t)stream>>>(h->P, tick, move_cnt, move_veh, move_node, stride);
+    dispatch_kernel<<<h->P.R, DISP_THREADS, 0, (cudaStream_t)stream>>>(h->P, tick, move_cnt, move_veh, move_node, stride);
     CKL("dispatch_kernel");
     return VDS_OK;
 }
@@ -1099,6 +1244,7 @@ int vds_rollout_is_fused(vds_handle h)
 }
 
 int vds_rollout_threads(vds_handle h) { return h ? h->roll_threads : 0; }
+const char *vds_rollout_kernel_name(vds_handle h) { (void)h; return "rollout_local_kernel"; }
 
 int vds_rollout(vds_handle h, int tick0, int nticks, void *stream)
 {
@@ -1168,6 +1314,63 @@ int vds_stats(vds_handle h, int64_t *out, void *stream)
     const int n = h->P.R * VDS_NUM_STATS;
     stats_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->P, (long long *)out);
     CKL("stats_kernel");
+    return VDS_OK;
+}
+
+
+int vds_bind_observations(vds_handle h, uint16_t *obs, int ring)
+{
+    if (!h || (obs && ring < 1)) return fail(h, VDS_ERR_INVALID, "vds_bind_observations: ring must be >= 1");
+    h->P.obs = obs; h->P.obs_ring = obs ? ring : 0;
+    return VDS_OK;
+}
+
+int vds_observe(vds_handle h, int tick, void *stream)
+{
+    int rc = ready(h, false); if (rc) return rc;
+    if (!h->P.obs) return fail(h, VDS_ERR_UNBOUND, "vds_observe: vds_bind_observations first");
+    if (tick < 0 || tick >= h->P.T) return fail(h, VDS_ERR_INVALID, "vds_observe: tick out of range");
+    dim3 grid((h->P.C + 127) / 128, h->P.R);
+    observe_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(h->P, tick);
+    CKL("observe_kernel");
+    return VDS_OK;
+}
+
+int vds_time_features(vds_handle h, int64_t t0_minutes, const float *weather60, const float *tmin30, const float *tmax30,
+                      const float *wdir30, const float *wpow30, float *out, void *stream)
+{
+    if (!h || !weather60 || !tmin30 || !tmax30 || !wdir30 || !wpow30 || !out)
+        return fail(h, VDS_ERR_INVALID, "vds_time_features: null pointer");
+    time_features_kernel<<<(h->P.T + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->P.T, (long long)t0_minutes, h->P.period,
+                                                                              weather60, tmin30, tmax30, wdir30, wpow30, out);
+    CKL("time_features_kernel");
+    return VDS_OK;
+}
+
+int vds_load_orders(vds_handle h, const int32_t *minute, const int32_t *pickup, const int32_t *delivery, int n,
+                    int drop_uncovered, int32_t *n_orders, void *stream)
+{
+    if (!h || !h->have_static || !h->have_orders || !h->have_sorted || !minute || !pickup || !delivery || !n_orders || n < 1)
+        return fail(h, VDS_ERR_INVALID, "vds_load_orders: bind_static / bind_orders (with the derived arrays) first");
+    if (h->P.OR != 1) return fail(h, VDS_ERR_INVALID, "vds_load_orders: needs one shared order stream (order_replicas == 1)");
+    cudaStream_t st = (cudaStream_t)stream;
+    const DevParams &P = h->P;
+    int *minute_kept = (int *)P.spd;                  // scratch: sorted_pd is rewritten by vds_prepare_orders
+    load_orders_kernel<<<1, LOAD_THREADS, 0, st>>>(P, minute, pickup, delivery, n, drop_uncovered, (uint32_t *)P.opd, minute_kept, n_orders);
+    CKL("load_orders_kernel");
+    tick_offsets_kernel<<<(P.T + 128) / 128, 128, 0, st>>>(P, minute_kept, n_orders, (int *)P.toff);
+    CKL("tick_offsets_kernel");
+    h->prepared = false;
+    return VDS_OK;
+}
+
+int vds_cluster_cost_sums(vds_handle h, const int32_t *cl_node_off, const uint16_t *cl_nodes, int64_t *out, void *stream)
+{
+    if (!h || !h->have_static || !cl_node_off || !cl_nodes || !out)
+        return fail(h, VDS_ERR_INVALID, "vds_cluster_cost_sums: bind_static first");
+    const long long pairs = (long long)h->P.C * h->P.C;
+    cluster_cost_sum_kernel<<<(unsigned)((pairs + 7) / 8), 256, 0, (cudaStream_t)stream>>>(h->P, cl_node_off, cl_nodes, (long long *)out);
+    CKL("cluster_cost_sum_kernel");
     return VDS_OK;
 }
 

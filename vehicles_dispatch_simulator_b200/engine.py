@@ -40,7 +40,9 @@ class City:
         self.nb_idx = np.asarray(nb_idx, np.int64)
         self.n_nodes = self.cost_u8.shape[0]
         self.n_clusters = len(self.nb_off) - 1
-        self.depth_limit = int(depth_limit)
+        # NeighborServerDeepLimit = int((Svc - Side/2) // Side) is -1 when Svc < Side/2: the DFS then returns at
+        # once and only the own cluster is matched (simulator.py:978-981) -- the same matches as limit 0
+        self.depth_limit = max(0, int(depth_limit))
         self.neighbor_can_server = bool(neighbor_can_server)
         self.cluster_nodes = cluster_nodes          # optional list of node arrays per cluster
         self._search = None
@@ -220,6 +222,8 @@ class DispatchEngine:
         per_tick = np.diff(off)
         if per_tick.max() > self.maxOT:
             raise N.VdsError(f"tick with {per_tick.max()} orders exceeds max_orders_per_tick={self.maxOT}")
+        self._check_nodes(order_pickup, "order pickup")
+        self._check_nodes(order_delivery, "order delivery")
         pd = (np.asarray(order_pickup, np.uint32) | (np.asarray(order_delivery, np.uint32) << 16)).astype(np.uint32)
         with torch.cuda.device(self.device):
             self.order_pd[0, :n] = torch.from_numpy(pd).to(self.device)
@@ -227,24 +231,107 @@ class DispatchEngine:
             self.n_orders_total[0] = n
             self._compute_values()
 
+    def _check_nodes(self, nodes, what):
+        """The reference raises KeyError (NodeID2Cluseter[node]) for a node outside every cluster; the kernels
+        index shared memory with the cluster id, so such a node must never reach them."""
+        a = np.asarray(nodes, np.int64).ravel()
+        bad = (a < 0) | (a >= self.city.n_nodes)
+        bad[~bad] = self.city.node2cluster[a[~bad]] < 0
+        if bad.any():
+            i = int(np.nonzero(bad)[0][0])
+            raise N.VdsError(f"{what} node {int(a[i])} (index {i}) belongs to no cluster "
+                             f"(the reference raises KeyError in NodeID2Cluseter here)")
+
+    def load_orders(self, order_minute, order_pickup, order_delivery, drop_uncovered=False):
+        """Reload / FocusOnLocalRegion on the device (simulator.py:130-212, 356-370): replace the shared order
+        stream; with drop_uncovered the orders whose pickup / delivery node lies outside every cluster are
+        compacted away by a kernel (vds_load_orders).  Returns the number of orders kept."""
+        assert self.OR == 1
+        m = np.asarray(order_minute, np.int32)
+        n = len(m)
+        if n > self.Nmax:
+            raise N.VdsError(f"order stream of {n} orders exceeds max_orders={self.Nmax}")
+        assert (np.diff(m) >= 0).all(), "orders must be sorted by release minute"
+        if not drop_uncovered:
+            self._check_nodes(order_pickup, "order pickup")
+            self._check_nodes(order_delivery, "order delivery")
+        dev = self.device
+        with torch.cuda.device(dev):
+            t = lambda a: torch.from_numpy(np.ascontiguousarray(a, np.int32)).to(dev)
+            dm, dp, dd = t(m), t(order_pickup), t(order_delivery)
+            self._ck(self.L.vds_load_orders(self.h, _ptr(dm), _ptr(dp), _ptr(dd), n, int(bool(drop_uncovered)),
+                                            _ptr(self.n_orders_total), self._stream()))
+            kept = int(self.n_orders_total[0].item())
+            per_tick = int((self.tick_off[0, 1:] - self.tick_off[0, :-1]).max().item())
+            if per_tick > self.maxOT:
+                raise N.VdsError(f"tick with {per_tick} orders exceeds max_orders_per_tick={self.maxOT}")
+            self._compute_values()
+        return kept
+
+    # --------------------------------------------------------- observations
+    def bind_observations(self, ring=None):
+        """Allocate + bind the observation ring (u16 [R, ring, 4, C]; include/vds.h): every tick's per-cluster
+        (idle before match, demand, SupplyExpect, idle after match).  ring defaults to the whole episode."""
+        ring = self.T if ring is None else int(ring)
+        self.obs = torch.zeros((self.R, ring, 4, self.nC), dtype=torch.uint16, device=self.device)
+        self._ck(self.L.vds_bind_observations(self.h, _ptr(self.obs), ring))
+        return self.obs
+
+    def unbind_observations(self):
+        self._ck(self.L.vds_bind_observations(self.h, None, 0))
+        self.obs = None
+
+    def observe(self, k):
+        """Pack tick k's observation after the per-phase calls (the fused kernels write it themselves)."""
+        self._ck(self.L.vds_observe(self.h, int(k), self._stream()))
+
+    def time_features(self, t0_minutes, tables):
+        """GetTimeAndWeather (simulator.py:842-866) for every tick's start time -> f32 [T, 10] device tensor.
+        tables: (WeatherType[60], MinimumTemperature[30], MaximumTemperature[30], WindDirection[30], WindPower[30])."""
+        dev = self.device
+        tt = [torch.as_tensor(np.asarray(a, np.float32), device=dev) for a in tables]
+        assert [len(x) for x in tt] == [60, 30, 30, 30, 30]
+        out = torch.empty((self.T, 10), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            self._ck(self.L.vds_time_features(self.h, C.c_int64(int(t0_minutes)), *[_ptr(x) for x in tt], _ptr(out),
+                                              self._stream()))
+        self._tf_tables = tt
+        return out
+
+    def cluster_cost_sums(self):
+        """int64 [C, C] device tensor: sum of RoadCost(k, l) over k in Nodes(i), l in Nodes(j)
+        (the O(C^2 n^2) loop of CreateCluster, simulator.py:594-631, as one kernel)."""
+        p = self._policy_tables()
+        out = torch.zeros((self.nC, self.nC), dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            self._ck(self.L.vds_cluster_cost_sums(self.h, _ptr(p["noff"]), _ptr(p["nflat"]), _ptr(out), self._stream()))
+        return out
+
     def _compute_values(self):
         """Order values + the per-(tick, cluster) layout the fused rollout reads
         (one pass over the stream; once per stream, not per tick)."""
         self._ck(self.L.vds_prepare_orders(self.h, _ptr(self.n_orders_total), self._stream()))
 
-    def generate_orders(self, tables, seed=1234, first_replica=0):
+    def generate_orders(self, tables, seed=1234, first_replica=0, check=True):
         """Per-replica synthetic Didi-shaped streams, generated on device
-        (Philox4x32-10 keyed by global replica id; see synthetic.DemandTables)."""
+        (Philox4x32-10 keyed by global replica id; see synthetic.DemandTables).  check=False skips the two
+        host read-backs of the capacity checks (an RL loop that regenerates streams every episode with tables it
+        has already sized the engine for)."""
         assert self.OR == self.R
         dev = self.device
         with torch.cuda.device(dev):
-            t = tables.to_device(dev)
-            self._gen_tables = t            # keep alive
+            if getattr(self, "_gen_tables_src", None) is not tables:
+                self._gen_tables = tables.to_device(dev)            # keep alive; uploaded once per table set
+                self._gen_tables_src = tables
+            t = self._gen_tables
             self._ck(self.L.vds_generate_orders(
                 self.h, C.c_uint64(seed), C.c_int64(first_replica), _ptr(t["slot_cdf"]), _ptr(t["slot_base"]),
                 tables.n_slots, tables.cdf_len, _ptr(t["zipf_cdf"]), tables.n_rank, _ptr(t["perm_pick"]),
                 _ptr(t["perm_drop"]), _ptr(self.order_pd), _ptr(self.tick_off), _ptr(self.n_orders_total),
                 self._stream()))
+            if not check:
+                self._compute_values()
+                return
             nmax = int(self.n_orders_total.max().item())
             if nmax > self.Nmax:
                 raise N.VdsError(f"generated {nmax} orders > max_orders={self.Nmax}")
@@ -274,6 +361,8 @@ class DispatchEngine:
             t = t.unsqueeze(0).expand(self.R, self.V)
         t = t.contiguous()
         assert t.shape == (self.R, self.V)
+        if t is not veh_loc0:                       # host-provided placement: validate (device tensors are trusted)
+            self._check_nodes(np.asarray(veh_loc0.cpu() if isinstance(veh_loc0, torch.Tensor) else veh_loc0), "vehicle placement")
         self._loc0 = t
         self._done_upto = 0          # ticks [0, _done_upto) have been matched since this reset
         with torch.cuda.device(self.device):
@@ -367,6 +456,10 @@ class DispatchEngine:
     @property
     def rollout_threads(self):
         return int(self.L.vds_rollout_threads(self.h))
+
+    @property
+    def rollout_kernel_name(self):
+        return self.L.vds_rollout_kernel_name(self.h).decode()
 
     def stats(self):
         """int64 [R, 10] device tensor (see _native.STAT_NAMES)."""

@@ -18,7 +18,7 @@ dispatch mutations (IdleVehicles.remove + VehiclesArrivetime[v] = t, the
 primitive implied by simulator.py:805-808, 889, 1018) are read back and applied
 on the device through vds_dispatch.
 
-Extra (non-reference) kwargs: replicas, device, data_dir, build_engine.
+Extra (non-reference) kwargs: replicas, device, data_dir, build_engine, reject_threshold, refresh_objects.
 """
 import datetime as dt
 import os
@@ -40,7 +40,7 @@ _PHASES = ("UpdateFunction", "MatchFunction", "SupplyExpectFunction")
 class Simulation(object):
     def __init__(self, ClusterMode, DemandPredictionMode, DispatchMode, VehiclesNumber, TimePeriods,
                  LocalRegionBound, SideLengthMeter, VehiclesServiceMeter, NeighborCanServer, FocusOnLocalRegion,
-                 replicas=1, device=0, data_dir=None, build_engine=True, reject_threshold=None):
+                 replicas=1, device=0, data_dir=None, build_engine=True, reject_threshold=None, refresh_objects=True):
         self.DispatchModule = None
         self.DemandPredictorModule = None
 
@@ -91,9 +91,6 @@ class Simulation(object):
 
         self.NeighborCanServer = NeighborCanServer
         self.FocusOnLocalRegion = FocusOnLocalRegion
-        if FocusOnLocalRegion:
-            raise NotImplementedError("FocusOnLocalRegion sub-box filtering is outside the accelerated path "
-                                      "(SURVEY.md section 2 row 16)")
 
         self.RealExpTime = None
         self.NowOrder = None
@@ -112,7 +109,12 @@ class Simulation(object):
         self.build_engine = build_engine
         self.view_replica = 0
         self.reject_threshold = int(PICKUPTIMEWINDOW.astype("int64")) if reject_threshold is None else int(reject_threshold)
-        self.period_min = int(np.timedelta64(TimePeriods).astype("int64")) // MINUTES
+        # TimePeriods is the reference's generic-unit timedelta64 (nanoseconds, config/setting.py:5); unit-typed
+        # timedelta64 / datetime.timedelta / pd.Timedelta values are accepted like its Timestamp arithmetic does
+        self.period_min = int(pd.Timedelta(TimePeriods) // pd.Timedelta(minutes=1))
+        if self.period_min < 9:
+            raise N.VdsError(f"TimePeriods={TimePeriods!r} is {self.period_min} minutes; the packed arrival key needs >= 9")
+        self.refresh_objects = bool(refresh_objects)
         self.engine = None
         self.city = None
         self._dirty = True
@@ -191,6 +193,8 @@ class Simulation(object):
 
         print("Create Orders set")
         self._make_orders(Orders)
+        if self.FocusOnLocalRegion:
+            print("Remove out-of-bounds Orders")
 
         Vehicles = Vehicles[:self.VehiclesNumber]
         print("Create Vehicles set")
@@ -199,12 +203,28 @@ class Simulation(object):
         self._build_engine()
 
     def _make_orders(self, Orders):
+        """Order objects (simulator.py:325), the FocusOnLocalRegion filter (:329-337) and OrderValue (:341-342).
+        Also keeps the stream as NumPy arrays: `_raw_stream` as loaded (what the device-side compaction of
+        vds_load_orders consumes) and `_minute / _pickup / _delivery` of the orders that remain."""
         ni = self._node_index
         self.Orders = [Order(i[0], i[1], ni[int(i[2])], ni[int(i[3])], i[1] + PICKUPTIMEWINDOW, None, None, None) for i in Orders]
+        times = pd.DatetimeIndex([o.ReleasTime for o in self.Orders])
+        minute = np.asarray((times - times[0]) // pd.Timedelta(minutes=1), np.int32)
+        pick = np.array([o.PickupPoint for o in self.Orders], np.int32)
+        drop = np.array([o.DeliveryPoint for o in self.Orders], np.int32)
+        self._raw_stream = (minute, pick, drop)
+        if self.FocusOnLocalRegion:
+            # IsOrderInLimitRegion (simulator.py:356-362): both end points inside a cluster of the region
+            covered = np.zeros(len(self.NodeIDList), bool)
+            covered[list(self.NodeID2NodesLocation.keys())] = True
+            keep = covered[pick] & covered[drop]
+            self.Orders = [o for o, k in zip(self.Orders, keep.tolist()) if k]
+            for i, o in enumerate(self.Orders):
+                o.ID = i
+            minute, pick, drop = minute[keep] - minute[keep][0], pick[keep], drop[keep]
+        self._minute, self._pickup, self._delivery = minute, pick, drop
         print("Pre-calculated order value")
         A = self._cost_table()
-        pick = np.array([o.PickupPoint for o in self.Orders], np.int64)
-        drop = np.array([o.DeliveryPoint for o in self.Orders], np.int64)
         for o, v in zip(self.Orders, A[drop, pick].tolist()):                # RoadCost(pickup, delivery)
             o.OrderValue = int(v)
 
@@ -232,9 +252,23 @@ class Simulation(object):
             self.engine.reset(self._placement)
             self._dirty = True
 
+    def IsOrderInLimitRegion(self, Order):
+        return Order.PickupPoint in self.NodeID2NodesLocation and Order.DeliveryPoint in self.NodeID2NodesLocation
+
+    def IsNodeInLimitRegion(self, TempNodeList):
+        lon, lat = TempNodeList[0][0], TempNodeList[0][1]
+        b = self.LocalRegionBound
+        return not (lon < b[0] or lon > b[1] or lat < b[2] or lat > b[3])
+
     def _node_locations(self):
+        """Node coordinates / ids in Node.csv order; FocusOnLocalRegion keeps only the nodes inside
+        LocalRegionBound (simulator.py:382-402, 542-563)."""
         loc = self.Node[['Longitude', 'Latitude']].values.round(7)
         ids = self.Node['NodeID'].values.astype('int64')
+        if self.FocusOnLocalRegion:
+            b = self.LocalRegionBound
+            keep = ~((loc[:, 0] < b[0]) | (loc[:, 0] > b[1]) | (loc[:, 1] < b[2]) | (loc[:, 1] > b[3]))
+            loc, ids = loc[keep], ids[keep]
         return loc, ids
 
     def CreateGrid(self):
@@ -282,20 +316,15 @@ class Simulation(object):
         NeighborPath = self._data(str(self.LocalRegionBound) + str(self.ClustersNumber) + str(self.ClusterMode) + 'Neighbor.csv')
         if not os.path.exists(NeighborPath):
             print("Computing Neighbor relationships between clusters")
-            A = self._cost_table().astype(np.int64)
+            sums = self._cluster_cost_sums(Clusters)                          # sum of RoadCost(k, l), k in i, l in j
             rows = []
             for i in Clusters:
-                ni = np.array([k[0] for k in i.Nodes], np.int64)
                 lst = []
                 for j in Clusters:
                     if i is j:
                         continue
-                    nj = np.array([k[0] for k in j.Nodes], np.int64)
-                    if len(ni) * len(nj) == 0:
-                        d = 99999
-                    else:
-                        d = A[np.ix_(nj, ni)].sum() / (len(ni) * len(nj))      # sum RoadCost(k, l) = A[l, k]
-                    lst.append((j.ID, d))
+                    cnt = len(i.Nodes) * len(j.Nodes)
+                    lst.append((j.ID, 99999 if cnt == 0 else int(sums[i.ID, j.ID]) / cnt))
                 lst.sort(key=lambda X: X[1])
                 rows.append(lst)
             pd.DataFrame(rows).to_csv(NeighborPath, header=0, index=0)
@@ -314,6 +343,30 @@ class Simulation(object):
                 self.NodeID2NodesLocation[j[0]] = j[1]
         return Clusters
 
+    def _cluster_cost_sums(self, Clusters):
+        """int64 [C, C]: sum of RoadCost(k, l) over k in Nodes(i), l in Nodes(j) -- the O(C^2 n^2) double loop of
+        simulator.py:594-617.  With a GPU engine enabled this is one kernel (vds_cluster_cost_sums) over the
+        uint8 cost table already needed in HBM; host-only instances (build_engine=False) use NumPy block sums."""
+        A = self._cost_table()
+        nodes = [np.array([k[0] for k in c.Nodes], np.int64) for c in Clusters]
+        if self.build_engine:
+            from .engine import City, DispatchEngine
+            n2c = np.full(A.shape[0], -1, np.int64)
+            for c, nd in zip(Clusters, nodes):
+                n2c[nd] = c.ID
+            tmp = DispatchEngine(City(A, n2c, np.zeros(len(Clusters) + 1, np.int64), [], cluster_nodes=nodes), 8,
+                                 replicas=1, ticks=1, max_orders=1, max_orders_per_tick=1, device=self.device)
+            sums = tmp.cluster_cost_sums().cpu().numpy()
+            tmp.close()
+            return sums
+        A = A.astype(np.int64)
+        sums = np.zeros((len(Clusters), len(Clusters)), np.int64)
+        for i, ni in enumerate(nodes):
+            for j, nj in enumerate(nodes):
+                if len(ni) and len(nj):
+                    sums[i, j] = A[np.ix_(nj, ni)].sum()                      # RoadCost(k, l) = A[l, k]
+        return sums
+
     # ------------------------------------------------------------------ engine
     def _build_engine(self):
         from .engine import City, DispatchEngine, tick_offsets
@@ -326,25 +379,42 @@ class Simulation(object):
         for c in self.Clusters:
             idx += [n.ID for n in c.Neighbor]
             off.append(len(idx))
-        self.city = City(self._cost_table(), n2c, off, idx, depth_limit=self.NeighborServerDeepLimit,
-                         neighbor_can_server=self.NeighborCanServer,
-                         cluster_nodes=[np.array([n[0] for n in c.Nodes], np.int64) for c in self.Clusters])
-        t0 = self.Orders[0].ReleasTime
-        self._minute = np.array([(o.ReleasTime - t0) // pd.Timedelta(minutes=1) for o in self.Orders], np.int32)
-        self._pickup = np.array([o.PickupPoint for o in self.Orders], np.int32)
-        self._delivery = np.array([o.DeliveryPoint for o in self.Orders], np.int32)
+        if getattr(self, "_city_key", None) != (id(self.Clusters), id(self.Map)):
+            self._city_key = (id(self.Clusters), id(self.Map))
+            self.city = None
+        if self.city is None:                       # Reload keeps the city (and the engine bound to it)
+            nodes = [np.array([n[0] for n in c.Nodes], np.int64) for c in self.Clusters]
+            self.city = City(self._cost_table(), n2c, off, idx, depth_limit=self.NeighborServerDeepLimit,
+                             neighbor_can_server=self.NeighborCanServer, cluster_nodes=nodes)
+        bad = self._placement[n2c[self._placement] < 0] if len(self._placement) else []
+        if len(bad):
+            raise N.VdsError(f"vehicle placed on node {int(bad[0])}, which belongs to no cluster")
         self._tick_off, self._T = tick_offsets(self._minute, self.period_min)
         self._pick_cluster = n2c[self._pickup]
         if not self.build_engine:
             return
-        if self.engine is not None:
-            self.engine.close()
-        self.engine = DispatchEngine(self.city, len(self.Vehicles), replicas=self.replicas, period=self.period_min,
-                                     ticks=self._T, max_orders=len(self.Orders),
-                                     max_orders_per_tick=max(64, int(np.diff(self._tick_off).max())),
-                                     reject_threshold=self.reject_threshold, device=self.device)
-        self.engine.bind_shared_orders(self._minute, self._pickup, self._delivery)
-        self.engine.reset(self._placement)
+        n_raw = len(self._raw_stream[0])
+        per_tick = max(64, int(np.diff(self._tick_off).max()))
+        e = self.engine
+        if e is not None and (e.T != self._T or e.Nmax < n_raw or e.maxOT < per_tick or e.V != len(self.Vehicles)
+                              or e.city is not getattr(self, "_engine_city", None)):
+            e.close()
+            e = self.engine = None
+        if e is None:
+            # head-room so that Reload() of another day swaps the stream on the device without a new engine
+            e = self.engine = DispatchEngine(self.city, len(self.Vehicles), replicas=self.replicas, period=self.period_min,
+                                             ticks=self._T, max_orders=n_raw + n_raw // 4 + 64,
+                                             max_orders_per_tick=per_tick + per_tick // 2,
+                                             reject_threshold=self.reject_threshold, device=self.device)
+            self._engine_city = self.city
+        if self.FocusOnLocalRegion:
+            # region filter as a device-side compaction of the stream as loaded
+            kept = e.load_orders(*self._raw_stream, drop_uncovered=True)
+            if kept != len(self.Orders):
+                raise N.VdsError(f"device-side order compaction kept {kept} orders, host filter {len(self.Orders)}")
+        else:
+            e.load_orders(self._minute, self._pickup, self._delivery)
+        e.reset(self._placement)
         self._dirty = True
 
     def _need_engine(self):
@@ -381,6 +451,9 @@ class Simulation(object):
         self.InitVehiclesIntoCluster()
 
     def Reload(self, OrderFileDate="1101"):
+        """Another day's orders (simulator.py:130-212).  The city, the engine and its HBM buffers stay; the new
+        stream is swapped in on the device (vds_load_orders: upload, FocusOnLocalRegion compaction, tick
+        offsets; vds_prepare_orders) -- a new engine is built only if the day does not fit the old buffers."""
         print("Load order " + OrderFileDate + "and reset the experimental environment")
         self._zero_counters()
         path = os.path.join(self.data_dir or os.path.join(os.getcwd(), "data"), "test", "order_2016" + str(OrderFileDate) + ".csv")
@@ -391,7 +464,7 @@ class Simulation(object):
             i.Reset()
         for i in self.Vehicles:
             i.Reset()
-        eng, self.engine = self.engine, None
+        eng, self.engine = self.engine, None          # placement first (it resets the engine when one is attached)
         self.InitVehiclesIntoCluster()
         self.engine = eng
         self._build_engine()
@@ -478,12 +551,31 @@ class Simulation(object):
         self._dirty = True
 
     def _push_dispatch(self, before):
-        """Read the agent's list/dict mutations back and replay them on the device."""
+        """Read the agent's list/dict mutations back and replay them on the device.  `before`: per cluster the
+        {vehicle: arrival time} table as it was when the hook started.  The device computes the arrival itself
+        (RealExpTime + RoadCost(LocationNode, DeliveryPoint) minutes, the primitive implied by simulator.py:805-808,
+        889, 1018), so an agent that enters a different time -- or re-times an existing entry -- would silently
+        diverge from what it wrote: that is an error here."""
         moves = []
         for c in self.Clusters:
-            for v in c.VehiclesArrivetime:
-                if v not in before[c.ID]:
-                    moves.append((self._vindex[id(v)], v.DeliveryPoint))
+            old = before[c.ID]
+            for v, when in c.VehiclesArrivetime.items():
+                if v in old:
+                    if when != old[v]:
+                        raise N.VdsError(f"DispatchFunction re-timed vehicle {v.ID} in Clusters[{c.ID}].VehiclesArrivetime; "
+                                         "only new entries (dispatches of idle vehicles) can be applied on the device")
+                    continue
+                if v.DeliveryPoint is None:
+                    raise N.VdsError(f"DispatchFunction put vehicle {v.ID} into Clusters[{c.ID}].VehiclesArrivetime "
+                                     "without setting Vehicle.DeliveryPoint")
+                node = int(v.DeliveryPoint)
+                if int(self.city.node2cluster[node]) != c.ID:
+                    raise N.VdsError(f"vehicle {v.ID}: DeliveryPoint {node} is not a node of Clusters[{c.ID}]")
+                expect = self.RealExpTime + np.timedelta64(self.RoadCost(v.LocationNode, node) * MINUTES)
+                if when != expect:
+                    raise N.VdsError(f"vehicle {v.ID}: arrival time {when} differs from RealExpTime + RoadCost "
+                                     f"({expect}); the device applies the road cost")
+                moves.append((self._vindex[id(v)], node))
         if not moves:
             return
         e = self._need_engine()
@@ -553,6 +645,14 @@ class Simulation(object):
             self.RealExpTime = self._tick_time(self._T)
             self.NowOrder = self.Orders[int(self._tick_off[self._T])]
             self.SupplyExpect = e.tensors["supply"][self.view_replica].cpu().numpy().astype(np.float64)
+            if self.refresh_objects:
+                # leave Orders / Clusters / Vehicles populated like the reference does after an episode
+                # (Order.ArriveInfo / PickupWaitTime, Cluster.IdleVehicles / VehiclesArrivetime, Vehicle.LocationNode ...)
+                self.step = self._T - 1
+                self._matched_this_tick = True
+                self._dirty = True
+                self._pull()
+                self.step = self._T
         else:
             def timed(acc, fn, pull):
                 if pull and self._overridden(fn.__name__):
@@ -581,7 +681,7 @@ class Simulation(object):
                     pd_ = e.tensors["per_dispatch"][self.view_replica].cpu().numpy()
                     for i in self.Clusters:
                         i.PerDispatchIdleVehicles = int(pd_[i.ID])
-                    before = {c.ID: set(c.VehiclesArrivetime.keys()) for c in self.Clusters}
+                    before = {c.ID: dict(c.VehiclesArrivetime) for c in self.Clusters}
                     t0 = dt.datetime.now()
                     self.DispatchFunction()
                     self._push_dispatch(before)
