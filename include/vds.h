@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define VDS_ABI_VERSION 4
+#define VDS_ABI_VERSION 5
 
 typedef enum vds_status {
     VDS_OK = 0,
@@ -152,6 +152,26 @@ const char *vds_last_error(vds_handle h);
 int  vds_bind_static(vds_handle h, const vds_static *s);
 int  vds_bind_orders(vds_handle h, const vds_orders *o);
 int  vds_bind_state(vds_handle h, const vds_state *s);
+
+/* ---- optional inputs of the node-queue rollout kernel (csrc/rollout_nq.cuh) ------------------------------
+ * RoadCost(vehicle.LocationNode, pickup) depends on the vehicle's node only and the reference's argmin is first-
+ * encountered under strict < (simulator.py:928-933), so of the idle vehicles standing on one node only the one
+ * earliest in Cluster.IdleVehicles order can win: the kernel keeps one FIFO queue per node and an order scans the
+ * nodes of its cluster instead of every idle vehicle.
+ *   vds_bind_cluster_nodes: Cluster.Nodes as CSR (cl_node_off i32[C+1], cl_nodes u16 in the reference's list order),
+ *       node_local u8[nodes] = index of a node inside its cluster's list (any value for uncovered nodes).
+ *   vds_bind_queues: per-replica queue links kept in HBM between windows: q_next u16[R][Vp] (next vehicle in the
+ *       queue, circular), q_tail u16[R][vds_padded_nodes(nodes)] (last vehicle of the node's queue, 0xFFFF = empty).
+ *       Caller-owned scratch; contents are meaningful only to the library.
+ * With both bound (and the own-cluster match, prepared orders, a replica fitting one SM's shared memory) vds_rollout
+ * / vds_tick launch rollout_nq_kernel while the links describe the vehicle table: straight after vds_reset, or after
+ * a previous node-queue window.  Any other call that changes vehicles (vds_update, vds_match, vds_dispatch*,
+ * vds_rollout_policy_random) sends vds_rollout back to rollout_local_kernel until the next vds_reset.  Results are
+ * bit-identical either way.  16-byte aligned device pointers. */
+int  vds_padded_nodes(int nodes);
+int  vds_bind_cluster_nodes(vds_handle h, const int32_t *cl_node_off, const uint16_t *cl_nodes, const uint8_t *node_local,
+                            int max_nodes_per_cluster);
+int  vds_bind_queues(vds_handle h, uint16_t *q_next, uint16_t *q_tail);
 
 /* order_value[i] = cost_u8[delivery][pickup] and value_total, on device
  * (replaces the OrderValue pre-computation loop, simulator.py:341-342). */

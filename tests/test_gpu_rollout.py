@@ -11,10 +11,14 @@ from tests.helpers import (SMALL_CASES, golden_city, load_golden, lockstep, make
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True)
-def _fused_search(monkeypatch):
-    """the speculative replica-resident search variant is opt-in (read by vds_create); these tests cover it"""
+@pytest.fixture(autouse=True, params=["node_queues", "slot_lists"])
+def _fused_search(monkeypatch, request):
+    """the speculative replica-resident search variant is opt-in (read by vds_create); these tests cover it.  Every
+    test runs twice: with the node-queue rollout kernel (csrc/rollout_nq.cuh, opt-in)
+    and with the per-cluster slot-list kernel (csrc/rollout.cuh) that is the default (the default; VDS_NQ=1 opts into the former)."""
     monkeypatch.setenv("VDS_FUSED_SEARCH", "1")
+    if request.param == "node_queues":
+        monkeypatch.setenv("VDS_NQ", "1")
 
 
 def _city(side=800, service=800, ncs=False, n_nodes=700):

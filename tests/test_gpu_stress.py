@@ -17,6 +17,13 @@ N_CASES = int(os.environ.get("VDS_STRESS_CASES", "24"))
 CASES = sorted(set(range(N_CASES)) | {211})
 
 
+@pytest.fixture(autouse=True, params=["node_queues", "slot_lists"])
+def _rollout_kernel(monkeypatch, request):
+    """both replica-resident kernels: rollout_nq_kernel (VDS_NQ=1) and rollout_local_kernel (default)"""
+    if request.param == "node_queues":
+        monkeypatch.setenv("VDS_NQ", "1")
+
+
 @pytest.mark.timeout(120)
 @pytest.mark.parametrize("case", CASES)
 def test_random_rollout_configuration(cuda_device, case):

@@ -59,7 +59,7 @@ EXPORTS = ("vds_abi_version", "vds_padded_vehicles", "vds_create", "vds_destroy"
            "vds_bind_static", "vds_bind_orders", "vds_bind_state", "vds_compute_order_values",
            "vds_prepare_orders", "vds_reset", "vds_clear_results", "vds_update", "vds_match", "vds_supply_expect", "vds_dispatch", "vds_dispatch_strided", "vds_policy_random", "vds_rollout_policy_random", "vds_rollout", "vds_tick", "vds_rollout_is_fused", "vds_rollout_threads",
            "vds_stats", "vds_sync", "vds_launch_count", "vds_generate_orders", "vds_generate_placement",
-           "vds_rollout_kernel_name", "vds_bind_observations", "vds_observe", "vds_time_features", "vds_load_orders", "vds_cluster_cost_sums")
+           "vds_rollout_kernel_name", "vds_padded_nodes", "vds_bind_cluster_nodes", "vds_bind_queues", "vds_bind_observations", "vds_observe", "vds_time_features", "vds_load_orders", "vds_cluster_cost_sums")
 
 
 def build(force=False, verbose=False):
@@ -113,6 +113,9 @@ def lib():
         "vds_rollout_is_fused": (C.c_int, [vp]),
         "vds_rollout_threads": (C.c_int, [vp]),
         "vds_rollout_kernel_name": (C.c_char_p, [vp]),
+        "vds_padded_nodes": (C.c_int, [i32]),
+        "vds_bind_cluster_nodes": (C.c_int, [vp, vp, vp, vp, i32]),
+        "vds_bind_queues": (C.c_int, [vp, vp, vp]),
         "vds_stats": (C.c_int, [vp, vp, vp]),
         "vds_sync": (C.c_int, [vp, vp]),
         "vds_launch_count": (i64, [vp]),

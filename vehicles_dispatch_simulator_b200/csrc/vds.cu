@@ -43,6 +43,8 @@
 struct RollLayout {
     int key, ent, arrive, node, clus, icnt, ioff, wtot, ooff, acc, wl, wl_ix, wl_pd, wl_cnt, wla, total;
 };
+// shared-memory layout of rollout_nq_kernel (rollout_nq.cuh)
+struct NqLayout { int key, arr, node, nxt, tail, icnt, occ, ooff, wl, wl2, q, acc, misc, total, qcap; };
 struct DevParams {
     int R, V, Vp, C, nodes, Nmax, T, period, depth, ncs, OR, maxOT; unsigned period_magic;
     long long threshold;
@@ -54,7 +56,10 @@ struct DevParams {
     // derived order layout (vds_prepare_orders) + optional rollout trace
     const uint32_t *spd; const uint16_t *sord; const uint16_t *coff; const long long *tick_value; int *trace;
     uint16_t *obs; int obs_ring;             // optional observation ring (vds_bind_observations): [R][ring][4][C] u16
-    RollLayout L;
+    // node-queue rollout kernel: Cluster.Nodes as CSR + node -> index inside its cluster; persisted queue links
+    const int *cl_off; const uint16_t *cl_nodes; const uint8_t *node_local; int W, nodes_pad;
+    uint16_t *q_next, *q_tail;
+    RollLayout L; NqLayout NQ;
 };
 
 struct vds_handle_s {
@@ -62,6 +67,9 @@ struct vds_handle_s {
     DevParams P;
     bool have_static, have_orders, have_state, have_sorted, prepared, fused_search;
     int roll_threads, roll_smem;
+    int nq_threads, nq_smem;                 // node-queue kernel: CTA width (0 = unavailable) and dynamic shared memory
+    int nq_state;                            // 0 stale (HBM queue links do not describe the vehicle table), 1 fresh reset, 2 valid
+    bool nq_off;
     int n_sidx, n_ridx;                      // search-list sizes: decide the shared-memory staging of match_search_kernel
     char err[512];
     int64_t launches;
@@ -720,6 +728,7 @@ struct RollPolicy {
 };
 
 #include "rollout.cuh"
+#include "rollout_nq.cuh"
 
 // ------------------------------------------- synthetic Didi-shaped generator
 // smallest j with u < cdf[j]  (cdf non-decreasing, cdf[n-1] == 0xFFFFFFFF catches everything)
@@ -1020,6 +1029,8 @@ int vds_create(const vds_config *cfg, vds_handle *out)
     const int prep_smem = (int)sizeof(int) * (2 * Cp + 4 + 16 + PREP_WARPS * Cp);
     CK(cudaFuncSetAttribute(prepare_orders_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, prep_smem));
     { const char *e = getenv("VDS_FUSED_SEARCH"); h->fused_search = e && e[0] == '1'; }
+    { const char *e = getenv("VDS_NO_NQ"); h->nq_off = e && e[0] == '1'; }
+    P.nodes_pad = vds_padded_nodes(cfg->nodes);
     CK(cudaFuncSetAttribute(match_search_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(match_search_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     // replica-resident rollout kernel: pick the CTA width from how many replicas fit one SM
@@ -1095,6 +1106,55 @@ int vds_bind_state(vds_handle h, const vds_state *s)
     h->have_state = true; return VDS_OK;
 }
 
+// The node-queue kernel needs (a) Cluster.Nodes and (b) per-replica queue links in HBM.  Both optional: without
+// them vds_rollout keeps using rollout_local_kernel.
+static int nq_configure(vds_handle h)
+{
+    h->nq_threads = 0;
+    DevParams &P = h->P;
+    if (!P.cl_off || !P.q_next || h->nq_off) return VDS_OK;
+    P.NQ = nq_layout(P.Vp, P.C, P.nodes_pad, P.W);
+    h->nq_smem = P.NQ.total;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, h->cfg.device));
+    if (h->nq_smem > (int)prop.sharedMemPerBlockOptin) return VDS_OK;
+    const int per_sm = (int)prop.sharedMemPerMultiprocessor / (h->nq_smem + 1024);
+    h->nq_threads = per_sm >= 6 ? 128 : per_sm >= 3 ? 256 : per_sm >= 2 ? 512 : 1024;
+    { const char *e = getenv("VDS_NQ_THREADS");       // developer knob: force a CTA width
+      if (e && (atoi(e) == 128 || atoi(e) == 256 || atoi(e) == 512 || atoi(e) == 1024)) h->nq_threads = atoi(e); }
+    CK(cudaFuncSetAttribute(rollout_nq_kernel<128, 7, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->nq_smem));
+    CK(cudaFuncSetAttribute(rollout_nq_kernel<256, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->nq_smem));
+    CK(cudaFuncSetAttribute(rollout_nq_kernel<512, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->nq_smem));
+    CK(cudaFuncSetAttribute(rollout_nq_kernel<1024, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->nq_smem));
+    CK(cudaFuncSetAttribute(rollout_nq_kernel<128, 7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->nq_smem));
+    CK(cudaFuncSetAttribute(rollout_nq_kernel<256, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->nq_smem));
+    CK(cudaFuncSetAttribute(rollout_nq_kernel<512, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->nq_smem));
+    CK(cudaFuncSetAttribute(rollout_nq_kernel<1024, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->nq_smem));
+    return VDS_OK;
+}
+
+int vds_bind_cluster_nodes(vds_handle h, const int32_t *cl_node_off, const uint16_t *cl_nodes, const uint8_t *node_local,
+                           int max_nodes_per_cluster)
+{
+    if (!h || !cl_node_off || !cl_nodes || !node_local || max_nodes_per_cluster < 1)
+        return fail(h, VDS_ERR_INVALID, "vds_bind_cluster_nodes: bad arguments");
+    h->P.cl_off = max_nodes_per_cluster <= 256 ? cl_node_off : nullptr;      // node_local is a byte
+    h->P.cl_nodes = cl_nodes; h->P.node_local = node_local;
+    h->P.W = (max_nodes_per_cluster + 31) / 32;
+    return nq_configure(h);
+}
+
+int vds_bind_queues(vds_handle h, uint16_t *q_next, uint16_t *q_tail)
+{
+    if (!h || !q_next || !q_tail || (((uintptr_t)q_next | (uintptr_t)q_tail) & 15))
+        return fail(h, VDS_ERR_INVALID, "vds_bind_queues: null or misaligned pointer");
+    h->P.q_next = q_next; h->P.q_tail = q_tail;
+    h->nq_state = 0;
+    return nq_configure(h);
+}
+
+int vds_padded_nodes(int nodes) { return (nodes + 7) & ~7; }
+
 static int ready(vds_handle h, bool need_orders)
 {
     if (!h) return VDS_ERR_INVALID;
@@ -1149,6 +1209,7 @@ int vds_reset(vds_handle h, const uint16_t *veh_loc0, void *stream)
     if (t2 > tot) tot = t2;
     reset_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(P, veh_loc0);
     CKL("reset_kernel");
+    h->nq_state = 1;                       // every vehicle idle, keys = vehicle index: queues are built from scratch
     return VDS_OK;
 }
 
@@ -1167,6 +1228,7 @@ int vds_update(vds_handle h, int tick, void *stream)
     const int smem = (int)sizeof(int) * (4 * Cp + 8 + 16 + UPD_WARPS * Cp);
     update_kernel<<<h->P.R, UPD_THREADS, smem, (cudaStream_t)stream>>>(h->P, tick, local_mode(h) ? 1 : 0);
     CKL("update_kernel");
+    h->nq_state = 0;                       // vehicle table changed outside the node-queue kernel
     return VDS_OK;
 }
 
@@ -1175,6 +1237,7 @@ int vds_match(vds_handle h, int tick, void *stream)
     int rc = ready(h, true); if (rc) return rc;
     if (tick < 0 || tick >= h->P.T) return fail(h, VDS_ERR_INVALID, "vds_match: tick out of range");
     const DevParams &P = h->P;
+    h->nq_state = 0;
     if (local_mode(h)) {
         dim3 grid((P.C + 3) / 4, P.R);
         match_local_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(P, tick);
@@ -1208,6 +1271,7 @@ int vds_dispatch(vds_handle h, int tick, const int32_t *move_off, const int32_t 
     if (!move_off || (total_moves > 0 && (!move_veh || !move_node)))
         return fail(h, VDS_ERR_INVALID, "vds_dispatch: null pointer");
     if (total_moves <= 0) return VDS_OK;
+    h->nq_state = 0;
     dispatch_kernel<<<h->P.R, DISP_THREADS, 0, (cudaStream_t)stream>>>(h->P, tick, move_off, move_veh, move_node, 0);
     CKL("dispatch_kernel");
     return VDS_OK;
@@ -1219,6 +1283,7 @@ int vds_dispatch_strided(vds_handle h, int tick, const int32_t *move_cnt, const 
     int rc = ready(h, false); if (rc) return rc;
     if (!move_cnt || !move_veh || !move_node || stride < 1)
         return fail(h, VDS_ERR_INVALID, "vds_dispatch_strided: bad arguments");
+    h->nq_state = 0;
     dispatch_kernel<<<h->P.R, DISP_THREADS, 0, (cudaStream_t)stream>>>(h->P, tick, move_cnt, move_veh, move_node, stride);
     CKL("dispatch_kernel");
     return VDS_OK;
@@ -1238,19 +1303,52 @@ int vds_policy_random(vds_handle h, int tick, uint64_t seed, int64_t first_repli
     return VDS_OK;
 }
 
+// vds_rollout runs the node-queue kernel when the optional inputs are bound, the own-cluster match applies, and the
+// queue links in HBM describe the vehicle table (fresh after vds_reset, or left by the previous node-queue window)
+static bool nq_usable(vds_handle h)
+{
+    return h->prepared && h->nq_threads > 0 && local_mode(h) && h->nq_state != 0 && !h->nq_off;
+}
+
 int vds_rollout_is_fused(vds_handle h)
 {
     return h && h->prepared && h->roll_threads > 0 && (local_mode(h) || h->fused_search);
 }
 
-int vds_rollout_threads(vds_handle h) { return h ? h->roll_threads : 0; }
-const char *vds_rollout_kernel_name(vds_handle h) { (void)h; return "rollout_local_kernel"; }
+int vds_rollout_threads(vds_handle h)
+{
+    if (!h) return 0;
+    return (h->prepared && h->nq_threads > 0 && local_mode(h) && !h->nq_off) ? h->nq_threads : h->roll_threads;
+}
+const char *vds_rollout_kernel_name(vds_handle h)
+{
+    return (h && h->prepared && h->nq_threads > 0 && local_mode(h) && !h->nq_off) ? "rollout_nq_kernel" : "rollout_local_kernel";
+}
 
 int vds_rollout(vds_handle h, int tick0, int nticks, void *stream)
 {
     int rc = ready(h, true); if (rc) return rc;
     if (tick0 < 0 || nticks < 0 || tick0 + nticks > h->P.T) return fail(h, VDS_ERR_INVALID, "vds_rollout: tick range");
     if (nticks == 0) return VDS_OK;
+    if (nq_usable(h)) {
+        // node-queue formulation (rollout_nq.cuh): per-node FIFO queues that persist across ticks and windows
+        cudaStream_t st = (cudaStream_t)stream;
+        const int fresh = h->nq_state == 1;
+        const bool timeout = h->P.threshold < 255;     // cost bytes are <= 255: otherwise "cost > threshold" never fires
+#define NQ_LAUNCH(TH, MB) do { if (timeout) rollout_nq_kernel<TH, MB, true><<<h->P.R, TH, h->nq_smem, st>>>(h->P, tick0, nticks, fresh); \
+                               else rollout_nq_kernel<TH, MB, false><<<h->P.R, TH, h->nq_smem, st>>>(h->P, tick0, nticks, fresh); } while (0)
+        switch (h->nq_threads) {
+        case 128: NQ_LAUNCH(128, 7); break;
+        case 256: NQ_LAUNCH(256, 3); break;
+        case 1024: NQ_LAUNCH(1024, 1); break;
+        default:  NQ_LAUNCH(512, 1); break;
+        }
+#undef NQ_LAUNCH
+        CKL("rollout_nq_kernel");
+        h->nq_state = 2;
+        return VDS_OK;
+    }
+    h->nq_state = 0;
     if (vds_rollout_is_fused(h)) {
         cudaStream_t st = (cudaStream_t)stream;
         if (local_mode(h)) {
@@ -1273,7 +1371,12 @@ int vds_rollout(vds_handle h, int tick0, int nticks, void *stream)
     for (int k = tick0; k < tick0 + nticks; k++) {
         if ((rc = vds_update(h, k, stream))) return rc;
         if ((rc = vds_match(h, k, stream))) return rc;
+        if (h->P.obs) {                       // observation ring bound: every tick's record is observable
+            if ((rc = vds_supply_expect(h, k, stream))) return rc;
+            if ((rc = vds_observe(h, k, stream))) return rc;
+        }
     }
+    if (h->P.obs) return VDS_OK;
     // SupplyExpect is an output, nothing on the path reads it: like the fused kernel, a hook-free window computes
     // it only where it is observable -- after its last tick (and books the whole window's tick count there)
     supply_kernel<<<h->P.R, UPD_THREADS, sizeof(int) * h->P.C, (cudaStream_t)stream>>>(h->P, tick0 + nticks - 1, nticks);
@@ -1294,6 +1397,7 @@ int vds_rollout_policy_random(vds_handle h, int tick0, int nticks, uint64_t seed
         return fail(h, VDS_ERR_UNBOUND, "vds_rollout_policy_random: needs prepared orders and the own-cluster (depth 0) match; "
                                       "use vds_tick + vds_policy_random + vds_dispatch_strided per tick otherwise");
     if (nticks == 0) return VDS_OK;
+    h->nq_state = 0;
     RollPolicy pol; pol.seed = seed; pol.first_replica = first_replica; pol.prob_q32 = move_prob_q32;
     pol.nb_off = nb_off; pol.nb_idx = nb_idx; pol.cl_node_off = cl_node_off; pol.cl_nodes = cl_nodes;
     cudaStream_t st = (cudaStream_t)stream;

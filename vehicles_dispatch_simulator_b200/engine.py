@@ -12,6 +12,7 @@ Reset / InitVehiclesIntoCluster :214-258, end-of-episode SumOrderValue
 :1095-1100.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -114,7 +115,7 @@ def _ptr(t):
 class DispatchEngine:
     def __init__(self, city, n_vehicles, replicas=1, period=10, ticks=148, max_orders=1,
                  per_replica_orders=False, max_orders_per_tick=4096,
-                 reject_threshold=N.PARITY_THRESHOLD, device=0, trace=False):
+                 reject_threshold=N.PARITY_THRESHOLD, device=0, trace=False, node_queues=None):
         if not torch.cuda.is_available():
             raise N.VdsError("DispatchEngine needs a CUDA device (sm_100a); there is no CPU fallback")
         self.L = N.lib()
@@ -186,6 +187,24 @@ class DispatchEngine:
                           + [self.trace.data_ptr() if trace else None]))
             self._ck(self.L.vds_bind_state(self.h, C.byref(s)))
             self._stats_out = z((R, N.VDS_NUM_STATS), torch.int64)
+            # ---- optional inputs of the node-queue rollout kernel (csrc/rollout_nq.cuh): Cluster.Nodes + per-replica
+            #      queue links.  Opt-in (node_queues=True or VDS_NQ=1): bit-identical, but on the measured workloads the
+            #      per-cluster slot-list kernel is still the faster one (profiles/r2_nq_*.md)
+            if node_queues is None:
+                node_queues = os.environ.get("VDS_NQ") == "1"
+            if node_queues and not (city.neighbor_can_server and city.depth_limit > 0):
+                p = self._policy_tables()
+                local = np.zeros(city.n_nodes, np.uint8)
+                sizes = np.diff(p["noff"].cpu().numpy())
+                if len(sizes) and sizes.max() <= 256:
+                    for nd in self._cluster_node_lists():
+                        local[np.asarray(nd, np.int64)] = np.arange(len(nd), dtype=np.uint8)
+                    self.t_node_local = torch.from_numpy(local).to(dev)
+                    self._ck(self.L.vds_bind_cluster_nodes(self.h, _ptr(p["noff"]), _ptr(p["nflat"]), _ptr(self.t_node_local),
+                                                           int(max(1, sizes.max()))))
+                    self.q_next = z((R, Vp), torch.uint16)
+                    self.q_tail = z((R, self.L.vds_padded_nodes(city.n_nodes)), torch.uint16)
+                    self._ck(self.L.vds_bind_queues(self.h, _ptr(self.q_next), _ptr(self.q_tail)))
 
     # ------------------------------------------------------------- plumbing
     def _ck(self, rc):
@@ -389,11 +408,15 @@ class DispatchEngine:
             return
         self._ck(self.L.vds_dispatch(self.h, int(k), _ptr(mo), _ptr(mv), _ptr(mn), int(mv.numel()), self._stream()))
 
+    def _cluster_node_lists(self):
+        city = self.city
+        return city.cluster_nodes if city.cluster_nodes is not None else \
+            [np.nonzero(city.node2cluster == c)[0] for c in range(self.nC)]
+
     def _policy_tables(self):
         if getattr(self, "_pol", None) is None:
             city, dev = self.city, self.device
-            nodes = city.cluster_nodes if city.cluster_nodes is not None else \
-                [np.nonzero(city.node2cluster == c)[0] for c in range(self.nC)]
+            nodes = self._cluster_node_lists()
             noff = np.cumsum([0] + [len(n) for n in nodes]).astype(np.int32)
             nflat = (np.concatenate([np.asarray(n, np.int64) for n in nodes]) if noff[-1] else np.zeros(1, np.int64)).astype(np.uint16)
             t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
