@@ -594,7 +594,7 @@ def main():
     # ---- the full SURVEY 8d unit of work, device resident
     #  (a) fresh synthetic streams every episode: generator + prepare inside the timed region
     def episode_fresh():
-        eng.generate_orders(tables, seed=SEED, first_replica=shard.first_replica, check=False)
+        eng.generate_orders(tables, seed=SEED, first_replica=shard.first_replica, check=False, fused=True)
         run.episode(loc0)
 
     episode_fresh()
@@ -690,8 +690,8 @@ def main():
                                       "inputs": "as e2e plus every replica's order stream + tick offsets re-uploaded and "
                                                 "re-prepared every step"},
                 "value_fresh_streams": {"value": fresh_value, "unit": "env-steps/s",
-                                        "what": "per step: vds_generate_orders (Philox, per replica) + vds_prepare_orders + reset + "
-                                                "rollout + stats, all device-resident"},
+                                        "what": "per step: vds_generate_prepared_orders (Philox draw + pricing + per-(tick, cluster) grouping "
+                                                "of a fresh stream per replica, one fused kernel) + reset + rollout + stats, all device-resident"},
                 "value_traced": {"value": traced_value, "unit": "env-steps/s", "obs_bytes_per_step": obs_bytes,
                                  "what": "per step: reset + rollout writing every tick's [R,4,C] u16 observation record "
                                          "(idle before/after match, demand, SupplyExpect) + stats", "obs_checksum": obs_sum},

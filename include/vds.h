@@ -305,15 +305,26 @@ int64_t vds_launch_count(vds_handle h);
  * device.  See vds_gen.h-style arguments below; all tables are device pointers.
  *   slot_cdf   u32[n_slots][cdf_len]  Poisson CDF thresholds per 10-minute slot
  *   slot_base  i32[n_slots]           count represented by slot_cdf[.][0]
- *   zipf_cdf   u32[n_rank]            cumulative thresholds over rank
+ *   zipf_thr   u32[n_rank], zipf_alias u16[n_rank]   Walker alias tables of the rank law: with two 32-bit uniforms
+ *              (u0, u1): i = (u0 * n_rank) >> 32; rank = i if u1 < zipf_thr[i] else zipf_alias[i]
  *   perm_pick/perm_drop u16[n_rank]   rank -> node permutations
  * Outputs order_pd [R][N_max], tick_off [R][T+1], n_orders [R].
  * Replica r uses Philox4x32-10 keyed by (seed, first_replica + r): results do
  * not depend on how replicas are split across GPUs. */
 int  vds_generate_orders(vds_handle h, uint64_t seed, int64_t first_replica,
                          const uint32_t *slot_cdf, const int32_t *slot_base, int n_slots, int cdf_len,
-                         const uint32_t *zipf_cdf, int n_rank, const uint16_t *perm_pick, const uint16_t *perm_drop,
+                         const uint32_t *zipf_thr, const uint16_t *zipf_alias, int n_rank,
+                         const uint16_t *perm_pick, const uint16_t *perm_drop,
                          uint32_t *order_pd, int32_t *tick_off, int32_t *n_orders, void *stream);
+
+/* vds_generate_orders + vds_prepare_orders in ONE pass over the bound per-replica streams (the orders never make the
+ * HBM round trip between the two; bit-identical results): writes order_pd, tick_off, order_value, value_total and the
+ * derived sorted_pd / sorted_idx / cluster_off / tick_value of the bound vds_orders, and n_orders[R].  For RL loops
+ * that draw fresh synthetic streams every episode. */
+int  vds_generate_prepared_orders(vds_handle h, uint64_t seed, int64_t first_replica,
+                                  const uint32_t *slot_cdf, const int32_t *slot_base, int n_slots, int cdf_len,
+                                  const uint32_t *zipf_thr, const uint16_t *zipf_alias, int n_rank,
+                                  const uint16_t *perm_pick, const uint16_t *perm_drop, int32_t *n_orders, void *stream);
 
 /* Uniform placement of vehicles on cluster-covered nodes, Philox keyed like
  * the orders (the batched InitVehiclesIntoCluster, simulator.py:249-258).

@@ -1,5 +1,5 @@
-"""NumPy restatement of the on-device synthetic generator (Philox4x32-10 +
-inverse-CDF sampling).  TEST INFRASTRUCTURE ONLY: used by tests/ and bench.py's
+"""NumPy restatement of the on-device synthetic generator (Philox4x32-10;
+inverse-CDF sampling of the Poisson slot counts, alias sampling of the Zipf ranks).  TEST INFRASTRUCTURE ONLY: used by tests/ and bench.py's
 CPU legs to give the oracle the same order streams / placements the GPU
 generates.  Philox4x32-10 is the published Random123 algorithm (Salmon et al.,
 SC'11); known-answer vectors from the Random123 distribution are checked in
@@ -35,6 +35,12 @@ def cdf_search(cdf, u):
     return np.minimum(j, len(cdf) - 1)
 
 
+def alias_draw(tables, u0, u1):
+    """rank = i if u1 < thr[i] else alias[i], i = (u0 * n_rank) >> 32  (Walker's alias method, integer arithmetic)."""
+    i = ((np.asarray(u0, np.uint64) * np.uint64(tables.n_rank)) >> np.uint64(32)).astype(np.int64)
+    return np.where(np.asarray(u1, np.uint64) < tables.zipf_thr[i].astype(np.uint64), i, tables.zipf_alias[i].astype(np.int64))
+
+
 def replica_orders(tables, seed, g):
     """(minute, pickup, delivery) of global replica g, in generation order."""
     k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
@@ -48,9 +54,9 @@ def replica_orders(tables, seed, g):
         if n == 0:
             continue
         i = np.arange(n, dtype=np.uint64)
-        a, b, _, _ = philox4x32_10(i, sl | (1 << 16), g0, g1, k0, k1)
-        pick.append(tables.perm_pick[cdf_search(tables.zipf_cdf, a)])
-        drop.append(tables.perm_drop[cdf_search(tables.zipf_cdf, b)])
+        a, b, c, d = philox4x32_10(i, sl | (1 << 16), g0, g1, k0, k1)
+        pick.append(tables.perm_pick[alias_draw(tables, a, b)])
+        drop.append(tables.perm_drop[alias_draw(tables, c, d)])
         minute.append(np.full(n, 10 * sl, np.int32))
     return (np.concatenate(minute), np.concatenate(pick).astype(np.int32), np.concatenate(drop).astype(np.int32))
 

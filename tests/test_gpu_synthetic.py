@@ -61,3 +61,32 @@ def test_split_independence(cuda_device):
     for r in range(3):
         assert np.array_equal(ea.tensors["order_res"][3 + r, :na[3 + r]].cpu().numpy(),
                               eb.tensors["order_res"][r, :na[3 + r]].cpu().numpy())
+
+
+def test_fused_generate_prepare_equals_two_kernels(cuda_device):
+    """vds_generate_prepared_orders (generator + pricing + per-(tick, cluster) grouping in one kernel, LUT-accelerated CDF
+    search) writes bit-identical streams and derived arrays to vds_generate_orders + vds_prepare_orders."""
+    import torch
+    from vehicles_dispatch_simulator_b200.engine import DispatchEngine
+    from vehicles_dispatch_simulator_b200.synthetic import DemandTables, synthetic_grid_city
+    city = synthetic_grid_city(n_nodes=900)
+    tables = DemandTables(city, orders_per_day=40_000)
+    mk = lambda: DispatchEngine(city, 300, replicas=5, ticks=tables.ticks, max_orders=tables.max_orders, per_replica_orders=True,
+                                max_orders_per_tick=tables.max_orders_per_tick)
+    a, b = mk(), mk()
+    a.generate_orders(tables, seed=77, first_replica=9)
+    b.generate_orders(tables, seed=77, first_replica=9, fused=True)
+    n = a.n_orders_total.cpu().numpy()
+    assert np.array_equal(n, b.n_orders_total.cpu().numpy())
+    assert torch.equal(a.tick_off, b.tick_off) and torch.equal(a.value_total, b.value_total)
+    assert torch.equal(a.tick_value, b.tick_value) and torch.equal(a.cluster_off, b.cluster_off)
+    for r in range(5):
+        for name in ("order_pd", "order_value"):
+            assert torch.equal(getattr(a, name)[r, :n[r]], getattr(b, name)[r, :n[r]]), (name, r)
+        for name in ("sorted_pd", "sorted_idx"):
+            assert torch.equal(getattr(a, name)[r, :n[r] - 1], getattr(b, name)[r, :n[r] - 1]), (name, r)
+    loc0 = a.generate_placement(seed=77, first_replica=9)
+    for e in (a, b):
+        e.reset(loc0); e.rollout(0, e.T)
+    assert torch.equal(a.stats(), b.stats()) and torch.equal(a.tensors["order_res"], b.tensors["order_res"])
+    a.close(); b.close()

@@ -195,6 +195,17 @@ def test_demand_tables_shape():
     assert (np.diff(t.zipf_cdf.astype(np.int64)) >= 0).all()
     p = np.diff(np.concatenate([[0], t.zipf_cdf.astype(np.float64)])) / 2 ** 32
     assert p[0] > 5 * p[99]                               # heavy head (exponent 0.83)
+    # the alias tables the generator draws from encode the same law: P(rank j) = (thr[j] + sum over i with alias i -> j
+    # of (2^32 - thr[i])) / (n * 2^32)
+    thr, al = t.zipf_thr.astype(np.float64), t.zipf_alias.astype(np.int64)
+    q = thr.copy()
+    np.add.at(q, al, 4294967296.0 - thr)
+    assert np.abs(q / (t.n_rank * 4294967296.0) - p).max() < 1e-8
+    from oracle.synth_ref import alias_draw
+    rng = np.random.default_rng(0)
+    u = rng.integers(0, 2 ** 32, (2, 400_000), dtype=np.uint64)
+    emp = np.bincount(alias_draw(t, u[0], u[1]), minlength=t.n_rank) / 400_000
+    assert abs(emp[0] - p[0]) < 0.003 and abs(emp[:10].sum() - p[:10].sum()) < 0.005
 
 
 def test_bench_stdout_carries_only_the_json_line():

@@ -58,7 +58,7 @@ class State(C.Structure):
 EXPORTS = ("vds_abi_version", "vds_padded_vehicles", "vds_create", "vds_destroy", "vds_last_error",
            "vds_bind_static", "vds_bind_orders", "vds_bind_state", "vds_compute_order_values",
            "vds_prepare_orders", "vds_reset", "vds_clear_results", "vds_update", "vds_match", "vds_supply_expect", "vds_dispatch", "vds_dispatch_strided", "vds_policy_random", "vds_rollout_policy_random", "vds_rollout", "vds_tick", "vds_rollout_is_fused", "vds_rollout_threads",
-           "vds_stats", "vds_sync", "vds_launch_count", "vds_generate_orders", "vds_generate_placement",
+           "vds_stats", "vds_sync", "vds_launch_count", "vds_generate_orders", "vds_generate_prepared_orders", "vds_generate_placement",
            "vds_rollout_kernel_name", "vds_padded_nodes", "vds_bind_cluster_nodes", "vds_bind_queues", "vds_bind_observations", "vds_observe", "vds_time_features", "vds_load_orders", "vds_cluster_cost_sums")
 
 
@@ -119,7 +119,8 @@ def lib():
         "vds_stats": (C.c_int, [vp, vp, vp]),
         "vds_sync": (C.c_int, [vp, vp]),
         "vds_launch_count": (i64, [vp]),
-        "vds_generate_orders": (C.c_int, [vp, u64, i64, vp, vp, i32, i32, vp, i32, vp, vp, vp, vp, vp, vp]),
+        "vds_generate_orders": (C.c_int, [vp, u64, i64, vp, vp, i32, i32, vp, vp, i32, vp, vp, vp, vp, vp, vp]),
+        "vds_generate_prepared_orders": (C.c_int, [vp, u64, i64, vp, vp, i32, i32, vp, vp, i32, vp, vp, vp, vp]),
         "vds_generate_placement": (C.c_int, [vp, u64, i64, vp, i32, vp, vp]),
         "vds_bind_observations": (C.c_int, [vp, vp, i32]),
         "vds_observe": (C.c_int, [vp, i32, vp]),

@@ -56,6 +56,32 @@ __device__ __forceinline__ uint32_t smem_addr(const void *p) {
     return a;
 }
 
+// ---- TMA (bulk async copy) staging of the window-start vehicle table load / window-end write-back ------------------
+// cp.async.bulk moves a contiguous, 16-byte aligned run between HBM and shared memory without passing through
+// registers: one elected thread issues the copies, an mbarrier counts the bytes, nobody spends LDG/STS issue slots.
+__device__ __forceinline__ void tma_mbar_init(uint32_t mbar_sa, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar_sa), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_mbar_expect(uint32_t mbar_sa, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar_sa), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(uint32_t dst_sa, const void *src, uint32_t bytes, uint32_t mbar_sa) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst_sa), "l"(src), "r"(bytes), "r"(mbar_sa) : "memory");
+}
+__device__ __forceinline__ void tma_mbar_wait(uint32_t mbar_sa, uint32_t phase) {
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+                 :: "r"(mbar_sa), "r"(phase) : "memory");
+}
+__device__ __forceinline__ void tma_store_1d(void *dst, uint32_t src_sa, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(dst), "r"(src_sa), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_wait() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 __host__ __device__ inline RollLayout roll_layout(int Vp, int C)
 {
     const int Cp = (C + 3) & ~3;
@@ -307,8 +333,34 @@ rollout_local_kernel(DevParams P, int k0, int nticks, RollPolicy pol)
     const uint16_t *sidx_base = P.sord + (size_t)ro * P.Nmax;
     uint32_t *res_base = P.order_res + (size_t)r * P.Nmax;
 
-    // ---- window start: HBM vehicle table -> shared memory (128-bit coalesced)
-    {
+    // ---- window start: HBM vehicle table -> shared memory
+    __shared__ __align__(8) unsigned long long tma_mbar;
+    if (P.tma) {
+        // five bulk async copies (TMA) issued by one thread, 12 B per vehicle; LocationNode lands in node[], DeliveryPoint
+        // in the (still unused) idle-slot pool, then one shared-memory pass keeps the one that applies
+        const uint32_t mbar_sa = (uint32_t)__cvta_generic_to_shared(&tma_mbar);
+        if (tid == 0) tma_mbar_init(mbar_sa, 1);
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t b2 = 2u * (uint32_t)Vp;
+            tma_mbar_expect(mbar_sa, 6u * b2);
+            tma_load_1d(arrive_sa0, P.veh_arrive + vb, b2, mbar_sa);
+            tma_load_1d(sm_sa + (uint32_t)L.node, P.veh_loc + vb, b2, mbar_sa);
+            tma_load_1d(ent_sa0, P.veh_dest + vb, b2, mbar_sa);
+            tma_load_1d(sm_sa + (uint32_t)L.clus, P.veh_cluster + vb, b2, mbar_sa);
+            tma_load_1d(key_sa0, P.veh_key + vb, 2u * b2, mbar_sa);
+        }
+        if (tid < 8) acc[tid] = 0;
+        tma_mbar_wait(mbar_sa, 0);
+        for (int g = tid; g < ngroups; g += THREADS) {
+            U16x8 a, n, d; a.v = reinterpret_cast<uint4 *>(arrive)[g]; n.v = reinterpret_cast<uint4 *>(node)[g];
+            d.v = reinterpret_cast<uint4 *>(ent)[g];
+#pragma unroll
+            for (int j = 0; j < 8; j++) if (a.h[j] != IDLE16) n.h[j] = d.h[j];
+            reinterpret_cast<uint4 *>(node)[g] = n.v;
+        }
+    } else {
+        // 128-bit coalesced loads through registers
         const uint4 *g_arr = reinterpret_cast<const uint4 *>(P.veh_arrive + vb);
         const uint4 *g_loc = reinterpret_cast<const uint4 *>(P.veh_loc + vb);
         const uint4 *g_dst = reinterpret_cast<const uint4 *>(P.veh_dest + vb);
@@ -864,6 +916,19 @@ rollout_local_kernel(DevParams P, int k0, int nticks, RollPolicy pol)
         uint4 *g_dst = reinterpret_cast<uint4 *>(P.veh_dest + vb);
         uint4 *g_clu = reinterpret_cast<uint4 *>(P.veh_cluster + vb);
         uint4 *g_key = reinterpret_cast<uint4 *>(P.veh_key + vb);
+        if (P.tma) {
+            // arrive / cluster / key go back as they are: three bulk async stores (TMA) from shared memory.  (The
+            // shared-memory writes of the last tick are made visible to the async proxy first.)
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            if (tid == 0) {
+                const uint32_t b2 = 2u * (uint32_t)Vp;
+                tma_store_1d(P.veh_arrive + vb, arrive_sa0, b2);
+                tma_store_1d(P.veh_cluster + vb, sm_sa + (uint32_t)L.clus, b2);
+                tma_store_1d(P.veh_key + vb, key_sa0, 2u * b2);
+                tma_store_commit_wait();
+            }
+        }
         for (int g = tid; g < ngroups; g += THREADS) {
             U16x8 a, n, l, d; a.v = reinterpret_cast<uint4 *>(arrive)[g]; n.v = reinterpret_cast<uint4 *>(node)[g];
             l.v = g_loc[g];
@@ -874,10 +939,13 @@ rollout_local_kernel(DevParams P, int k0, int nticks, RollPolicy pol)
                 if (idle) l.h[j] = n.h[j];
                 d.h[j] = (idle || pad) ? (uint16_t)IDLE16 : n.h[j];
             }
-            g_arr[g] = a.v; g_loc[g] = l.v; g_dst[g] = d.v;
-            g_clu[g] = reinterpret_cast<uint4 *>(clus)[g];
-            g_key[2 * g] = reinterpret_cast<uint4 *>(key)[2 * g];
-            g_key[2 * g + 1] = reinterpret_cast<uint4 *>(key)[2 * g + 1];
+            g_loc[g] = l.v; g_dst[g] = d.v;
+            if (!P.tma) {
+                g_arr[g] = a.v;
+                g_clu[g] = reinterpret_cast<uint4 *>(clus)[g];
+                g_key[2 * g] = reinterpret_cast<uint4 *>(key)[2 * g];
+                g_key[2 * g + 1] = reinterpret_cast<uint4 *>(key)[2 * g + 1];
+            }
         }
         for (int d = 16; d; d >>= 1) {
             a_match += __shfl_xor_sync(FULL, a_match, d); a_wait += __shfl_xor_sync(FULL, a_wait, d);

@@ -34,6 +34,7 @@
 #include <new>
 
 #define IDLE16 0xFFFFu
+#define VDS_TMA_DEFAULT 1          // measured: profiles/r2_tma_experiment.md (VDS_TMA=0 selects the LDG->STS loops)
 #define DEAD32 0xFFFFFFFFu
 #define FULL 0xFFFFFFFFu
 #define UPD_THREADS 256
@@ -55,6 +56,7 @@ struct DevParams {
     long long *stats; uint2 *idle_ent; int *idle_off, *bucket_off; uint16_t *bucket_ord; int *disp_seq;
     // derived order layout (vds_prepare_orders) + optional rollout trace
     const uint32_t *spd; const uint16_t *sord; const uint16_t *coff; const long long *tick_value; int *trace;
+    int tma;                                 // window-start / window-end vehicle table copies as TMA bulk copies (VDS_TMA)
     uint16_t *obs; int obs_ring;             // optional observation ring (vds_bind_observations): [R][ring][4][C] u16
     // node-queue rollout kernel: Cluster.Nodes as CSR + node -> index inside its cluster; persisted queue links
     const int *cl_off; const uint16_t *cl_nodes; const uint8_t *node_local; int W, nodes_pad;
@@ -739,6 +741,15 @@ __device__ __forceinline__ int cdf_search(const uint32_t *cdf, int n, uint32_t u
     return lo;
 }
 
+// Walker's alias method on two 32-bit uniforms: i = (u0 * n) >> 32; i if u1 < thr[i] else alias[i].  Two independent
+// table reads (one round trip) instead of the 12 dependent probes of a CDF search.
+__device__ __forceinline__ int alias_draw(const uint32_t *__restrict__ thr, const uint16_t *__restrict__ alias, int n, uint32_t u0, uint32_t u1)
+{
+    const int i = (int)(((uint64_t)u0 * (uint64_t)n) >> 32);
+    const uint32_t t = thr[i]; const int a = alias[i];
+    return u1 < t ? i : a;
+}
+
 __global__ void gen_counts_kernel(DevParams P, uint64_t seed, long long first_replica,
                                   const uint32_t *slot_cdf, const int *slot_base, int n_slots, int cdf_len,
                                   int *tick_off, int *n_orders)
@@ -778,8 +789,8 @@ __global__ void gen_finalize_kernel(DevParams P, int *tick_off, const int *n_ord
 
 __global__ void gen_orders_kernel(DevParams P, uint64_t seed, long long first_replica,
                                   const uint32_t *slot_cdf, const int *slot_base, int n_slots, int cdf_len,
-                                  const uint32_t *zipf_cdf, int n_rank, const uint16_t *perm_pick, const uint16_t *perm_drop,
-                                  uint32_t *order_pd, const int *tick_off)
+                                  const uint32_t *zipf_thr, const uint16_t *zipf_alias, int n_rank,
+                                  const uint16_t *perm_pick, const uint16_t *perm_drop, uint32_t *order_pd, const int *tick_off)
 {
     const int r = blockIdx.y, s = blockIdx.x;
     const unsigned long long g = (unsigned long long)(first_replica + r);
@@ -788,10 +799,110 @@ __global__ void gen_orders_kernel(DevParams P, uint64_t seed, long long first_re
     for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
         if (off + i >= P.Nmax) break;
         Philox x = philox4x32_10((uint32_t)i, (uint32_t)s | (1u << 16), (uint32_t)g, (uint32_t)(g >> 32), (uint32_t)seed, (uint32_t)(seed >> 32));
-        const int pr = cdf_search(zipf_cdf, n_rank, x.c[0]);
-        const int dr = cdf_search(zipf_cdf, n_rank, x.c[1]);
+        const int pr = alias_draw(zipf_thr, zipf_alias, n_rank, x.c[0], x.c[1]);
+        const int dr = alias_draw(zipf_thr, zipf_alias, n_rank, x.c[2], x.c[3]);
         order_pd[(size_t)r * P.Nmax + off + i] = (uint32_t)perm_pick[pr] | ((uint32_t)perm_drop[dr] << 16);
     }
+}
+
+
+// --------------------------------------------- fused generator + order preparation (fresh streams every episode)
+// gen_orders_kernel + prepare_orders_kernel in one pass: a CTA owns one (tick, replica), draws the tick's orders
+// (same Philox counters, same CDF searches -- bit-identical streams), prices them (RoadCost(pickup, delivery),
+// simulator.py:341-342) and emits them twice: in stream order (order_pd, order_value) and stably grouped by pickup
+// cluster (sorted_pd / sorted_idx / cluster_off, the layout the rollout kernels read).  The orders never make the
+// HBM round trip between the two kernels.  Runs between gen_counts_kernel and gen_finalize_kernel.
+#define GP_THREADS 128
+#define GP_WARPS (GP_THREADS / 32)
+__global__ void __launch_bounds__(GP_THREADS)
+gen_prepare_kernel(DevParams P, uint64_t seed, long long first_replica, int n_slots,
+                   const uint32_t *__restrict__ zipf_thr, const uint16_t *__restrict__ zipf_alias, int n_rank,
+                   const uint16_t *__restrict__ perm_pick, const uint16_t *__restrict__ perm_drop,
+                   uint32_t *order_pd, const int *tick_off, const int *n_orders, uint8_t *oval, long long *vtotal,
+                   uint32_t *spd, uint16_t *sidx, uint16_t *coff_out, long long *tick_value)
+{
+    extern __shared__ int sm[];
+    const int C = P.C, Cp = (C + 3) & ~3;
+    int *ocnt = sm;                     // [Cp]
+    int *boff = ocnt + Cp;              // [Cp+4]
+    int *wtot = boff + Cp + 4;          // [16]
+    int *whist = wtot + 16;             // [GP_WARPS][Cp]
+    uint32_t *pd_s = reinterpret_cast<uint32_t *>(whist + GP_WARPS * Cp);            // [maxOT] the tick's orders
+    uint16_t *c_s = reinterpret_cast<uint16_t *>(pd_s + P.maxOT);                    // [maxOT] their pickup clusters
+    uint16_t *rk_s = c_s + ((P.maxOT + 1) & ~1);                                     // [maxOT] rank inside (warp segment, cluster)
+    __shared__ long long s_val;
+    const int k = blockIdx.x, r = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const unsigned long long g = (unsigned long long)(first_replica + r);
+    const int *to = tick_off + (size_t)r * (P.T + 1);                                // un-clamped offsets (gen_counts_kernel)
+    const int off = to[k], cnt_all = to[min(k + 1, P.T)] - off;
+    const int total = min(n_orders[r], P.Nmax);
+    const int lim = total > 0 ? total - 1 : 0;                                       // the last order is never consumed (Q8)
+    const int cnt = max(0, min(cnt_all, P.Nmax - off));                              // generated here
+    const int n = min(P.maxOT, max(0, min(off + cnt, lim) - min(off, lim)));         // consumed by tick k (staged in shared memory)
+    const int s = k - 1;                                                             // slot s feeds tick s + 1
+    for (int i = tid; i < Cp; i += GP_THREADS) ocnt[i] = 0;
+    for (int i = tid; i < GP_WARPS * Cp; i += GP_THREADS) whist[i] = 0;
+    if (tid == 0) s_val = 0;
+    __syncthreads();
+    long long vs = 0, vs_tick = 0;
+    const int seg = ((cnt + GP_WARPS - 1) / GP_WARPS + 31) & ~31;                    // per-warp contiguous segment
+    const int s0 = w * seg, s1 = min(cnt, s0 + seg);
+    int *mywh = whist + w * Cp;
+    uint32_t *g_pd = order_pd + (size_t)r * P.Nmax + off;
+    uint8_t *g_val = oval + (size_t)r * P.Nmax + off;
+    for (int base = s0; base < s1; base += 32) {
+        const int i = base + lane;
+        const bool valid = i < s1;
+        uint32_t pd = 0; int v = 0, c = 0;
+        if (valid) {
+            const Philox x = philox4x32_10((uint32_t)i, (uint32_t)s | (1u << 16), (uint32_t)g, (uint32_t)(g >> 32), (uint32_t)seed, (uint32_t)(seed >> 32));
+            const uint32_t pn = perm_pick[alias_draw(zipf_thr, zipf_alias, n_rank, x.c[0], x.c[1])];
+            const uint32_t dn = perm_drop[alias_draw(zipf_thr, zipf_alias, n_rank, x.c[2], x.c[3])];
+            pd = pn | (dn << 16);
+            v = P.cost[(size_t)dn * P.nodes + pn];                                    // RoadCost(pickup, delivery)
+            c = P.n2c[pn];
+            g_pd[i] = pd; g_val[i] = (uint8_t)v;
+            vs += v;
+        }
+        // stable rank of the order inside (this warp's segment, its cluster): orders are visited in index order
+        const bool cons = valid && i < n;
+        const unsigned cm = __ballot_sync(FULL, cons);
+        if (cons) {
+            vs_tick += v;
+            const unsigned peers = __match_any_sync(cm, c);
+            const int leader = __ffs(peers) - 1;
+            int start = 0;
+            if (lane == leader) { start = mywh[c]; mywh[c] = start + __popc(peers); }
+            start = __shfl_sync(peers, start, leader);
+            pd_s[i] = pd; c_s[i] = (uint16_t)c; rk_s[i] = (uint16_t)(start + __popc(peers & lanemask_lt()));
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    for (int c = tid; c < C; c += GP_THREADS) {
+        int run = 0;
+#pragma unroll
+        for (int ww = 0; ww < GP_WARPS; ww++) { const int t = whist[ww * Cp + c]; whist[ww * Cp + c] = run; run += t; }
+        ocnt[c] = run;
+    }
+    __syncthreads();
+    block_exclusive_scan(ocnt, boff, C, wtot);
+    uint16_t *g_coff = coff_out + ((size_t)r * P.T + k) * (C + 1);
+    for (int i = tid; i <= C; i += GP_THREADS) g_coff[i] = (uint16_t)boff[i];
+    const int tb = min(off, lim);                                                    // the clamped tick offset the rollout uses
+    uint32_t *g_spd = spd + (size_t)r * P.Nmax + tb;
+    uint16_t *g_sidx = sidx + (size_t)r * P.Nmax + tb;
+    // scatter: position = cluster offset + orders of the cluster in earlier warps' segments + rank inside the segment
+    for (int i = tid; i < n; i += GP_THREADS) {
+        const int c = c_s[i];
+        const int ww = min(i / max(seg, 1), GP_WARPS - 1);
+        const int pos = boff[c] + whist[ww * Cp + c] + rk_s[i];
+        g_spd[pos] = pd_s[i]; g_sidx[pos] = (uint16_t)i;
+    }
+    for (int d = 16; d; d >>= 1) { vs += __shfl_xor_sync(FULL, vs, d); vs_tick += __shfl_xor_sync(FULL, vs_tick, d); }
+    if (lane == 0) { if (vs) atomicAddLL(vtotal + r, vs); if (vs_tick) atomicAddLL(&s_val, vs_tick); }
+    __syncthreads();
+    if (tid == 0) tick_value[(size_t)r * P.T + k] = s_val;
 }
 
 __global__ void gen_placement_kernel(DevParams P, uint64_t seed, long long first_replica,
@@ -1030,6 +1141,7 @@ int vds_create(const vds_config *cfg, vds_handle *out)
     CK(cudaFuncSetAttribute(prepare_orders_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, prep_smem));
     { const char *e = getenv("VDS_FUSED_SEARCH"); h->fused_search = e && e[0] == '1'; }
     { const char *e = getenv("VDS_NO_NQ"); h->nq_off = e && e[0] == '1'; }
+    { const char *e = getenv("VDS_TMA"); P.tma = e ? (e[0] == '1') : VDS_TMA_DEFAULT; }
     P.nodes_pad = vds_padded_nodes(cfg->nodes);
     CK(cudaFuncSetAttribute(match_search_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(match_search_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -1497,10 +1609,11 @@ int vds_debug_prof(unsigned long long *out16, int clear)     /* developer builds
 
 int vds_generate_orders(vds_handle h, uint64_t seed, int64_t first_replica,
                         const uint32_t *slot_cdf, const int32_t *slot_base, int n_slots, int cdf_len,
-                        const uint32_t *zipf_cdf, int n_rank, const uint16_t *perm_pick, const uint16_t *perm_drop,
+                        const uint32_t *zipf_thr, const uint16_t *zipf_alias, int n_rank,
+                        const uint16_t *perm_pick, const uint16_t *perm_drop,
                         uint32_t *order_pd, int32_t *tick_off, int32_t *n_orders, void *stream)
 {
-    if (!h || !slot_cdf || !slot_base || !zipf_cdf || !perm_pick || !perm_drop || !order_pd || !tick_off || !n_orders)
+    if (!h || !slot_cdf || !slot_base || !zipf_thr || !zipf_alias || !perm_pick || !perm_drop || !order_pd || !tick_off || !n_orders)
         return fail(h, VDS_ERR_INVALID, "vds_generate_orders: null pointer");
     if (n_slots < 1 || n_slots > 1024 || n_slots + 1 > h->P.T || cdf_len < 1 || n_rank < 1 || h->P.OR != h->P.R)
         return fail(h, VDS_ERR_INVALID, "vds_generate_orders: needs per-replica order streams and n_slots < ticks");
@@ -1509,10 +1622,42 @@ int vds_generate_orders(vds_handle h, uint64_t seed, int64_t first_replica,
     CKL("gen_counts_kernel");
     dim3 grid(n_slots, h->P.R);
     gen_orders_kernel<<<grid, 128, 0, st>>>(h->P, seed, first_replica, slot_cdf, slot_base, n_slots, cdf_len,
-                                            zipf_cdf, n_rank, perm_pick, perm_drop, order_pd, tick_off);
+                                            zipf_thr, zipf_alias, n_rank, perm_pick, perm_drop, order_pd, tick_off);
     CKL("gen_orders_kernel");
     gen_finalize_kernel<<<h->P.R, 128, 0, st>>>(h->P, tick_off, n_orders);
     CKL("gen_finalize_kernel");
+    return VDS_OK;
+}
+
+
+int vds_generate_prepared_orders(vds_handle h, uint64_t seed, int64_t first_replica,
+                                 const uint32_t *slot_cdf, const int32_t *slot_base, int n_slots, int cdf_len,
+                                 const uint32_t *zipf_thr, const uint16_t *zipf_alias, int n_rank,
+                                 const uint16_t *perm_pick, const uint16_t *perm_drop, int32_t *n_orders, void *stream)
+{
+    if (!h || !slot_cdf || !slot_base || !zipf_thr || !zipf_alias || !perm_pick || !perm_drop || !n_orders)
+        return fail(h, VDS_ERR_INVALID, "vds_generate_prepared_orders: null pointer");
+    if (!h->have_static || !h->have_orders || !h->have_sorted)
+        return fail(h, VDS_ERR_UNBOUND, "vds_generate_prepared_orders: bind_static / bind_orders (with the derived arrays) first");
+    if (n_slots < 1 || n_slots > 1024 || n_slots + 1 > h->P.T || cdf_len < 1 || n_rank < 1 || n_rank > 65535 || h->P.OR != h->P.R)
+        return fail(h, VDS_ERR_INVALID, "vds_generate_prepared_orders: needs per-replica order streams and n_slots < ticks");
+    cudaStream_t st = (cudaStream_t)stream;
+    const DevParams &P = h->P;
+    const int Cp = (P.C + 3) & ~3;
+    const size_t smem = sizeof(int) * (2 * Cp + 4 + 16 + GP_WARPS * Cp) + 4 * (size_t)P.maxOT + 4 * (size_t)((P.maxOT + 1) & ~1);
+    if (smem > 200 * 1024) return fail(h, VDS_ERR_INVALID, "vds_generate_prepared_orders: max_orders_per_tick too large for one CTA");
+    CK(cudaFuncSetAttribute(gen_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaMemsetAsync((void *)P.vtotal, 0, sizeof(int64_t) * P.OR, st));
+    gen_counts_kernel<<<P.R, UPD_THREADS, 0, st>>>(P, seed, first_replica, slot_cdf, slot_base, n_slots, cdf_len, (int *)P.toff, n_orders);
+    CKL("gen_counts_kernel");
+    dim3 grid(P.T, P.R);
+    gen_prepare_kernel<<<grid, GP_THREADS, smem, st>>>(P, seed, first_replica, n_slots, zipf_thr, zipf_alias, n_rank, perm_pick, perm_drop,
+                                                      (uint32_t *)P.opd, P.toff, n_orders, (uint8_t *)P.oval, (long long *)P.vtotal,
+                                                      (uint32_t *)P.spd, (uint16_t *)P.sord, (uint16_t *)P.coff, (long long *)P.tick_value);
+    CKL("gen_prepare_kernel");
+    gen_finalize_kernel<<<P.R, 128, 0, st>>>(P, (int *)P.toff, n_orders);
+    CKL("gen_finalize_kernel");
+    h->prepared = true;
     return VDS_OK;
 }
 

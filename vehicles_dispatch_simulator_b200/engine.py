@@ -331,7 +331,7 @@ class DispatchEngine:
         (one pass over the stream; once per stream, not per tick)."""
         self._ck(self.L.vds_prepare_orders(self.h, _ptr(self.n_orders_total), self._stream()))
 
-    def generate_orders(self, tables, seed=1234, first_replica=0, check=True):
+    def generate_orders(self, tables, seed=1234, first_replica=0, check=True, fused=False):
         """Per-replica synthetic Didi-shaped streams, generated on device
         (Philox4x32-10 keyed by global replica id; see synthetic.DemandTables).  check=False skips the two
         host read-backs of the capacity checks (an RL loop that regenerates streams every episode with tables it
@@ -343,9 +343,20 @@ class DispatchEngine:
                 self._gen_tables = tables.to_device(dev)            # keep alive; uploaded once per table set
                 self._gen_tables_src = tables
             t = self._gen_tables
+            if fused:
+                # generator + preparation in one kernel (fresh streams per episode): same streams, same derived layout
+                self._ck(self.L.vds_generate_prepared_orders(
+                    self.h, C.c_uint64(seed), C.c_int64(first_replica), _ptr(t["slot_cdf"]), _ptr(t["slot_base"]),
+                    tables.n_slots, tables.cdf_len, _ptr(t["zipf_thr"]), _ptr(t["zipf_alias"]), tables.n_rank,
+                    _ptr(t["perm_pick"]), _ptr(t["perm_drop"]), _ptr(self.n_orders_total), self._stream()))
+                if check:
+                    nmax = int(self.n_orders_total.max().item())
+                    if nmax > self.Nmax:
+                        raise N.VdsError(f"generated {nmax} orders > max_orders={self.Nmax}")
+                return
             self._ck(self.L.vds_generate_orders(
                 self.h, C.c_uint64(seed), C.c_int64(first_replica), _ptr(t["slot_cdf"]), _ptr(t["slot_base"]),
-                tables.n_slots, tables.cdf_len, _ptr(t["zipf_cdf"]), tables.n_rank, _ptr(t["perm_pick"]),
+                tables.n_slots, tables.cdf_len, _ptr(t["zipf_thr"]), _ptr(t["zipf_alias"]), tables.n_rank, _ptr(t["perm_pick"]),
                 _ptr(t["perm_drop"]), _ptr(self.order_pd), _ptr(self.tick_off), _ptr(self.n_orders_total),
                 self._stream()))
             if not check:
@@ -467,6 +478,17 @@ class DispatchEngine:
         """One fused tick (update + match + supply_expect)."""
         self._ck(self.L.vds_tick(self.h, int(k), self._stream()))
         self._done_upto = max(self._done_upto, int(k) + 1)
+
+    def capture_graph(self, fn):
+        """Capture the C-ABI launches (and any torch ops) that fn() issues on the current stream into ONE CUDA graph
+        and return it; graph.replay() then re-issues them with a single launch.  Typical use: the per-tick RL loop
+        `for k: tick(k); <policy network>; dispatch(...)` of a whole episode -- hundreds of launches -- when the hook
+        lives on the device.  fn must not synchronise or read anything back to the host."""
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.device(self.device), torch.cuda.graph(g):
+            fn()
+        return g
 
     def clear_results(self):
         """order_res := "not processed" everywhere (reset does not do it, see include/vds.h)."""

@@ -131,12 +131,32 @@ def synthetic_grid_city(side_m=800, service_m=800, neighbor_can_server=False, n_
     return city
 
 
+def alias_tables(p):
+    """Walker / Vose alias tables of the pmf p, quantised to integers: thr u32 (accept i when u1 < thr[i]) and alias u16."""
+    n = len(p)
+    q = np.asarray(p, np.float64) * n
+    alias = np.arange(n, dtype=np.int64)
+    prob = np.ones(n, np.float64)
+    small = [i for i in range(n) if q[i] < 1.0]
+    large = [i for i in range(n) if q[i] >= 1.0]
+    while small and large:
+        s_, l_ = small.pop(), large.pop()
+        prob[s_] = q[s_]
+        alias[s_] = l_
+        q[l_] = (q[l_] + q[s_]) - 1.0
+        (small if q[l_] < 1.0 else large).append(l_)
+    thr = np.minimum(np.floor(prob * 4294967296.0), 4294967295.0).astype(np.uint64)
+    return thr.astype(np.uint32), alias.astype(np.uint16)
+
+
 class DemandTables:
     """Integer sampling tables for the on-device generator.
 
     slot_cdf[s][j] = floor(P(Poisson(mean_s) <= slot_base[s] + j) * 2^32)
-    (last entry 0xFFFFFFFF); zipf_cdf[r] likewise for rank r with exponent 0.83;
-    perm_pick / perm_drop map rank -> node."""
+    (last entry 0xFFFFFFFF).  Ranks follow Zipf(0.83) and are drawn with Walker's alias method from two 32-bit
+    uniforms (u0, u1): i = (u0 * n_rank) >> 32; rank = i if u1 < zipf_thr[i] else zipf_alias[i]  -- two independent
+    table reads instead of a 12-step dependent CDF search.  perm_pick / perm_drop map rank -> node.
+    (zipf_cdf, the cumulative thresholds of the same law, is kept for reference / tests.)"""
 
     def __init__(self, city, orders_per_day=200_000, zipf_exponent=0.83, perm_seed=5, cdf_len=1024,
                  slot_counts=SHIPPED_SLOT_COUNTS):
@@ -159,6 +179,7 @@ class DemandTables:
         z = np.minimum(np.floor(c * 4294967296.0), 4294967295.0).astype(np.uint64)
         z[-1] = 0xFFFFFFFF
         self.zipf_cdf = z.astype(np.uint32)
+        self.zipf_thr, self.zipf_alias = alias_tables(p / p.sum())
         rng = np.random.default_rng(perm_seed)
         self.perm_pick = valid[rng.permutation(self.n_rank)].astype(np.uint16)
         self.perm_drop = valid[rng.permutation(self.n_rank)].astype(np.uint16)
@@ -170,4 +191,4 @@ class DemandTables:
     def to_device(self, device):
         import torch
         return {k: torch.from_numpy(getattr(self, k)).to(device)
-                for k in ("slot_cdf", "slot_base", "zipf_cdf", "perm_pick", "perm_drop")}
+                for k in ("slot_cdf", "slot_base", "zipf_thr", "zipf_alias", "perm_pick", "perm_drop")}
