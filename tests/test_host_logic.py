@@ -307,3 +307,42 @@ def test_engine_rejects_nodes_outside_every_cluster():
     for bad in ([0, 2], [4], [-1]):
         with pytest.raises(VdsError):
             eng._check_nodes(bad, "x")
+
+
+def test_setup_on_the_shipped_day_matches_reference_inputs():
+    """SURVEY 8f-2 (host packer): CreateAllInstantiate on the SHIPPED 2016-11-01 data (oracle/_ref/data, made by
+    oracle/make_ref.py) packs exactly the arrays the unmodified reference built (golden real_grid6000 inputs), with
+    column-wise order packing and the cached cost matrix; the wall time of both passes is printed."""
+    import zipfile
+    ref_data = os.path.join(ROOT, "oracle", "_ref", "data")
+    z = load_golden("grid6000", real=True)
+    if not os.path.isdir(ref_data) or z is None:
+        pytest.skip("oracle/_ref or tests/golden/_real not present")
+    d = "/tmp/vds_setup_test/data"
+    os.makedirs(d, exist_ok=True)
+    for name in os.listdir(ref_data):
+        src = os.path.join(ref_data, name)
+        if name.endswith(".zip"):
+            with zipfile.ZipFile(src) as zf:
+                for m in zf.namelist():
+                    if not os.path.exists(os.path.join(d, m)):
+                        zf.extract(m, d)
+        elif not os.path.exists(os.path.join(d, name)):
+            import shutil
+            shutil.copy(src, os.path.join(d, name))
+    os.environ["TZ"] = "UTC"
+    time.tzset()
+    walls = []
+    for _ in range(2):                                   # first pass may parse the 110 MB CSV, second uses the cache
+        sim = _bare_sim(VehiclesNumber=6000, data_dir=d)
+        random.seed(0)
+        t0 = time.perf_counter()
+        sim.CreateAllInstantiate()
+        walls.append(time.perf_counter() - t0)
+    print("CreateAllInstantiate wall (s):", walls)
+    assert np.array_equal(sim._minute, z["in_order_minute"]) and np.array_equal(sim._pickup, z["in_order_pickup"])
+    assert np.array_equal(sim._delivery, z["in_order_delivery"]) and np.array_equal(sim._placement, z["in_veh_loc0"])
+    assert np.array_equal(sim.city.node2cluster, z["in_node2cluster"]) and np.array_equal(sim.city.cost_u8, z["in_cost_u8"])
+    assert np.array_equal(sim.city.nb_off, z["in_nb_off"]) and np.array_equal(sim.city.nb_idx, z["in_nb_idx"])
+    assert np.array_equal([o.OrderValue for o in sim.Orders], z["in_order_value"])
+    assert walls[1] < 15.0

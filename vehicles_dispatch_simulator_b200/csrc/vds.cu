@@ -812,7 +812,7 @@ __global__ void gen_orders_kernel(DevParams P, uint64_t seed, long long first_re
 // simulator.py:341-342) and emits them twice: in stream order (order_pd, order_value) and stably grouped by pickup
 // cluster (sorted_pd / sorted_idx / cluster_off, the layout the rollout kernels read).  The orders never make the
 // HBM round trip between the two kernels.  Runs between gen_counts_kernel and gen_finalize_kernel.
-#define GP_THREADS 128
+#define GP_THREADS 256          // block_exclusive_scan is written for UPD_THREADS == 256
 #define GP_WARPS (GP_THREADS / 32)
 __global__ void __launch_bounds__(GP_THREADS)
 gen_prepare_kernel(DevParams P, uint64_t seed, long long first_replica, int n_slots,

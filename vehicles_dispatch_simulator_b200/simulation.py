@@ -206,12 +206,17 @@ class Simulation(object):
         """Order objects (simulator.py:325), the FocusOnLocalRegion filter (:329-337) and OrderValue (:341-342).
         Also keeps the stream as NumPy arrays: `_raw_stream` as loaded (what the device-side compaction of
         vds_load_orders consumes) and `_minute / _pickup / _delivery` of the orders that remain."""
-        ni = self._node_index
-        self.Orders = [Order(i[0], i[1], ni[int(i[2])], ni[int(i[3])], i[1] + PICKUPTIMEWINDOW, None, None, None) for i in Orders]
-        times = pd.DatetimeIndex([o.ReleasTime for o in self.Orders])
+        # column-wise (the reference does one NodeIDList.index() scan and one Timestamp addition per order)
+        index = pd.Index(np.asarray(self.NodeIDList, np.int64))
+        pick = index.get_indexer(Orders[:, 2].astype(np.int64)).astype(np.int32)
+        drop = index.get_indexer(Orders[:, 3].astype(np.int64)).astype(np.int32)
+        if (pick < 0).any() or (drop < 0).any():
+            raise ValueError("order references a node id that is not in NodeIDList")     # list.index() raises ValueError too
+        times = pd.DatetimeIndex(Orders[:, 1])
+        window = times + pd.Timedelta(PICKUPTIMEWINDOW)
         minute = np.asarray((times - times[0]) // pd.Timedelta(minutes=1), np.int32)
-        pick = np.array([o.PickupPoint for o in self.Orders], np.int32)
-        drop = np.array([o.DeliveryPoint for o in self.Orders], np.int32)
+        self.Orders = [Order(a, b, c, d, e, None, None, None)
+                       for a, b, c, d, e in zip(Orders[:, 0].tolist(), list(times), pick.tolist(), drop.tolist(), list(window))]
         self._raw_stream = (minute, pick, drop)
         if self.FocusOnLocalRegion:
             # IsOrderInLimitRegion (simulator.py:356-362): both end points inside a cluster of the region
