@@ -435,8 +435,8 @@ rollout_nq_kernel(DevParams P, int k0, int nticks, int fresh)
         cm.arr_sa = S.arr; cm.node_sa = S.node; cm.key_sa = S.key; cm.g_loc = P.veh_loc + vb; cm.res = res_base + tb;
         cm.k = k; cm.magic = P.period_magic; cm.pm1 = P.period - 1;
         // -- classify: clusters with orders AND idle vehicles.  ONE idle vehicle (the most common case): without a
-        //    timeout the cluster's first order takes it, no argmin.  <= 4 idle vehicles: back of the work list (one
-        //    THREAD each); the others: front of the list (one WARP each).
+        //    timeout the cluster's first order takes it, no argmin.  Idle vehicles on <= 4 nodes and <= 4 orders to serve:
+        //    back of the work list (one THREAD each); the others: front of the list (one WARP each).
         for (int c_l = tid; c_l < C; c_l += THREADS) {
             const uint32_t o0 = lds_u16(S.ooff + 2u * (uint32_t)c_l), o1 = lds_u16(S.ooff + 2u * (uint32_t)c_l + 2u);
             const int m_l = (int)(o1 - o0);
@@ -458,7 +458,8 @@ rollout_nq_kernel(DevParams P, int k0, int nticks, int fresh)
                     t_match++; t_wait += wait; t_val += o_val; t_look++;
                     sts_u32(S.icnt + 4u * (uint32_t)c_l, 0u);
                 } else {
-                    const bool lp = !TIMEOUT && n_l <= 4 && one_word;
+                    // one THREAD can match it when <= 4 of its nodes hold idle vehicles and <= 4 orders can be served
+                    const bool lp = !TIMEOUT && one_word && min(m_l, n_l) <= 4 && __popc(occ[c_l * W]) <= 4;
                     const uint32_t slot = lp ? (uint32_t)(C - 1) - atoms_add(S.misc + 24u, 1u) : atoms_add(S.misc + 20u, 1u);
                     sts_u16(S.wl + 2u * slot, (uint32_t)c_l);
                 }
@@ -538,13 +539,17 @@ rollout_nq_kernel(DevParams P, int k0, int nticks, int fresh)
                             }
                         }
                         const int cnt = min(32, steps - jb);
-                        // the cost byte depends on (pickup, node) only: the gather of order j + 1 is issued before order j
-                        // is resolved and stays valid whatever vehicle the node's queue then leads with
-                        uint32_t cnext = ldg_u8_if(cx + __shfl_sync(FULL, rowv, 0), alive, ROLL_DEAD);
+                        // the cost byte depends on (pickup, node) only: gathers of later orders are issued before order j is
+                        // resolved and stay valid whatever vehicle the node's queue then leads with
+                        // three gathers in flight: orders j, j + 1, j + 2 (most clusters serve <= 3 orders: one round trip)
+                        uint32_t c0 = ldg_u8_if(cx + __shfl_sync(FULL, rowv, 0), alive, ROLL_DEAD);
+                        uint32_t c1 = ldg_u8_if(cx + __shfl_sync(FULL, rowv, 1), alive, ROLL_DEAD);
+                        uint32_t c2 = ldg_u8_if(cx + __shfl_sync(FULL, rowv, 2), alive, ROLL_DEAD);
                         for (int j = 0; j < cnt; j++) {
-                            const uint32_t cst = cnext;
-                            // (lanes past the chunk hold row 0: a valid address; at j == 31 lane 0's row is re-read, unused)
-                            cnext = ldg_u8_if(cx + __shfl_sync(FULL, rowv, (j + 1) & 31), alive, ROLL_DEAD);
+                            const uint32_t cst = c0;
+                            // (lanes past the chunk hold row 0: a valid address; wrapped lanes re-read rows that are not used)
+                            c0 = c1; c1 = c2;
+                            c2 = ldg_u8_if(cx + __shfl_sync(FULL, rowv, (j + 3) & 31), alive, ROLL_DEAD);
                             const uint32_t mn = __reduce_min_sync(FULL, cst);
                             if constexpr (TIMEOUT) {
                                 if (lane == 0) t_look += (unsigned)live;
@@ -561,7 +566,7 @@ rollout_nq_kernel(DevParams P, int k0, int nticks, int fresh)
                             if (lane == j) { my_ex = wex; my_wait = mn; }
                             if (lane == win) {                               // IdleVehicles.remove (:963)
                                 hv = nq_pop(x, t, hv, hk, S);
-                                if (hv == NQ_NONE) { alive = false; cnext = ROLL_DEAD; }
+                                if (hv == NQ_NONE) { alive = false; c0 = ROLL_DEAD; c1 = ROLL_DEAD; c2 = ROLL_DEAD; }
                             }
                             live--;
                         }
