@@ -138,78 +138,71 @@ __device__ __forceinline__ uint32_t nq_pop(uint32_t x, uint32_t &t, uint32_t h, 
     return nh;
 }
 
-// A cluster with <= 4 idle vehicles (on <= 4 of its <= 32 nodes) is matched by ONE thread: all cost gathers of its
-// <= 4 x 4 (order, node) pairs are in flight at once, the greedy assignment runs in registers.  No timeout.
-// Kept out of line so its register footprint does not tax the warp-cooperative path.
-struct NqLaneArgs {              // passed BY VALUE (registers): a by-reference struct would live in local memory
-    uint32_t key, arr, node, nxt, tail, nodes_u, k, pm1, magic;
-    const uint32_t *spd_t; const uint16_t *sidx_t; const uint16_t *cl_nodes; const uint8_t *cost; uint16_t *g_loc; uint32_t *res;
-};
-__device__ __noinline__ uint4 nq_lane_match(NqLaneArgs a, int steps, int n_l, int b0_l, int off_c, uint32_t occ_sa, uint32_t icnt_sa)
+__device__ __forceinline__ uint4 lds_v4(uint32_t a) { uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; }
+
+// Arrivals due by tick kk (arrive tick <= kk, en route): queue them, bucketed by node % 4, for the appending warps.
+// Two u16 per 32-bit op: (0x8000 + kk) - (t & 0x7FFF) keeps bit 15 iff (t & 0x7FFF) <= kk and never borrows into the
+// other half; idle (0x4000 | link) and padding (0x7FFF) entries have bits 14..0 > kk.  With `sup` the order-carrying
+// ones are also counted per destination cluster: SupplyExpectFunction (simulator.py:880-891) of tick kk - 1 is exactly
+// "vehicles with an order that arrive by the start of the next slot".  Out of line: one copy for its three call sites.
+template <int THREADS>
+__device__ __noinline__ void nq_scan_arrivals(uint32_t arr_sa, uint32_t node_sa, uint32_t misc_sa, uint32_t q_sa, int ngroups,
+                                              int qcap, int kk, uint32_t *sup, const uint16_t *__restrict__ n2c)
 {
-    struct { NqSm S; const uint32_t *spd_t; const uint16_t *sidx_t; const uint16_t *cl_nodes; const uint8_t *cost; uint32_t nodes_u; } q;
-    q.S.key = a.key; q.S.arr = a.arr; q.S.node = a.node; q.S.nxt = a.nxt; q.S.tail = a.tail;
-    q.spd_t = a.spd_t; q.sidx_t = a.sidx_t; q.cl_nodes = a.cl_nodes; q.cost = a.cost; q.nodes_u = a.nodes_u;
-    NqCommit cm;
-    cm.arr_sa = a.arr; cm.node_sa = a.node; cm.key_sa = a.key; cm.g_loc = a.g_loc; cm.res = a.res;
-    cm.k = (int)a.k; cm.pm1 = (int)a.pm1; cm.magic = a.magic;
-    uint4 st = make_uint4(0, 0, 0, 0);                                // matches, wait, value, lookups
-    uint32_t x[4], t[4], hv[4], hk[4], pd[4], ix[4], val[4], cst[4][4]; int li[4];
-    uint32_t mask = lds_u32(occ_sa);
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        x[i] = 0; t[i] = NQ_NONE; hv[i] = NQ_NONE; hk[i] = ROLL_DEAD; li[i] = 0;
-        if (mask) { li[i] = __ffs(mask) - 1; mask &= mask - 1; x[i] = q.cl_nodes[off_c + li[i]]; }
-        else li[i] = -1;
-    }
-#pragma unroll
-    for (int i = 0; i < 4; i++) if (li[i] >= 0) { t[i] = lds_u16(q.S.tail + 2u * x[i]); }
-#pragma unroll
-    for (int i = 0; i < 4; i++) if (li[i] >= 0) { hv[i] = lds_u16(q.S.nxt + 2u * t[i]); }
-#pragma unroll
-    for (int i = 0; i < 4; i++) if (li[i] >= 0) { hk[i] = lds_u32(q.S.key + 4u * hv[i]); }
-#pragma unroll
-    for (int j = 0; j < 4; j++) { pd[j] = 0; ix[j] = 0; if (j < steps) { pd[j] = q.spd_t[b0_l + j]; ix[j] = q.sidx_t[b0_l + j]; } }
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        val[j] = 0;
-#pragma unroll
-        for (int i = 0; i < 4; i++) cst[j][i] = ROLL_DEAD;
-        if (j < steps) {
-            const uint32_t pn = pd[j] & 0xFFFF, dn = pd[j] >> 16;
-            const uint32_t rowoff = pn * q.nodes_u;
-            val[j] = q.cost[dn * q.nodes_u + pn];
-#pragma unroll
-            for (int i = 0; i < 4; i++) if (li[i] >= 0) cst[j][i] = q.cost[rowoff + x[i]];
-        }
-    }
-    int live = n_l;
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        if (j < steps) {
-            st.w += (uint32_t)live;
-            uint32_t best = ROLL_DEAD, bk = ROLL_DEAD; int bi = 0;
-#pragma unroll
-            for (int i = 0; i < 4; i++) if (hv[i] != NQ_NONE) {
-                const uint32_t c2 = cst[j][i];
-                if (c2 < best || (c2 == best && hk[i] < bk)) { best = c2; bk = hk[i]; bi = i; }
+    const uint32_t k2 = ((uint32_t)kk | 0x8000u) * 0x00010001u;
+    for (int g = threadIdx.x; g < ngroups; g += THREADS) {
+        const uint4 a = lds_v4(arr_sa + 16u * (uint32_t)g);
+        const uint32_t f0 = (k2 - (a.x & 0x7FFF7FFFu)) & 0x80008000u, f1 = (k2 - (a.y & 0x7FFF7FFFu)) & 0x80008000u;
+        const uint32_t f2 = (k2 - (a.z & 0x7FFF7FFFu)) & 0x80008000u, f3 = (k2 - (a.w & 0x7FFF7FFFu)) & 0x80008000u;
+        if (f0 | f1 | f2 | f3) {
+            // bit i: low half of word i (vehicle 2i), bit 16 + i: high half (vehicle 2i + 1)
+            uint32_t b = (f0 >> 15) | (f1 >> 14) | (f2 >> 13) | (f3 >> 12);
+            while (b) {
+                const int p = __ffs(b) - 1; b &= b - 1;
+                const uint32_t v = (uint32_t)(g * 8 + (p < 16 ? 2 * p : 2 * (p - 16) + 1));
+                const uint32_t x = lds_u16(node_sa + 2u * v);
+                const uint32_t qi = x & (NQ_QUEUES - 1);
+                const uint32_t pos = atoms_add(misc_sa + 4u * qi, 1u);
+                if (pos < (uint32_t)qcap) sts_u16(q_sa + 2u * (qi * (uint32_t)qcap + pos), v);
+                if (sup && (lds_u16(arr_sa + 2u * v) & 0x8000u)) atomicAdd(&sup[n2c[x]], 1u);
             }
-            uint32_t bx = x[0], bt = t[0], bh = hv[0], bhk = hk[0];
-#pragma unroll
-            for (int i = 1; i < 4; i++) if (bi == i) { bx = x[i]; bt = t[i]; bh = hv[i]; bhk = hk[i]; }
-            cm.commit(bh | (bx << 16), best, val[j], pd[j] >> 16, ix[j]);
-            bh = nq_pop(bx, bt, bh, bhk, q.S);
-#pragma unroll
-            for (int i = 0; i < 4; i++) if (bi == i) { t[i] = bt; hv[i] = bh; hk[i] = bhk; }
-            st.x++; st.y += best; st.z += val[j]; live--;
         }
     }
-    uint32_t occ_new = 0;
-#pragma unroll
-    for (int i = 0; i < 4; i++) if (hv[i] != NQ_NONE) occ_new |= 1u << li[i];
-    sts_u32(occ_sa, occ_new);
-    sts_u32(icnt_sa, (uint32_t)live);
-    return st;
+}
+
+// Per-cluster observables of one tick where they are observable (last tick of a window, trace / observation ring bound).
+// Out of line: cold in the hook-free replay, and the hot loop stays small.
+struct NqEmit { int *a, *b; int *tr; uint16_t *ob; };       // two i32[C] outputs, trace row, observation row (or NULL)
+template <int THREADS>
+__device__ __noinline__ void nq_emit_before_match(NqEmit e, const uint32_t *icnt, const uint16_t *ooff, int C)
+{   // PerMatchIdleVehicles (simulator.py:909-910), len(Cluster.Orders)
+    for (int i = threadIdx.x; i < C; i += THREADS) {
+        const int iv = (int)icnt[i], no = (int)ooff[i + 1] - (int)ooff[i];
+        e.a[i] = iv; e.b[i] = no;
+        if (e.tr) { e.tr[i] = iv; e.tr[3 * C + i] = no; }
+        if (e.ob) { e.ob[i] = (uint16_t)iv; e.ob[C + i] = (uint16_t)no; }
+    }
+}
+template <int THREADS>
+__device__ __noinline__ void nq_emit_after_match(NqEmit e, const uint32_t *icnt, uint32_t *sup, int C)
+{   // PerDispatchIdleVehicles / LaterDispatchIdleVehicles (:1080-1087); clears the SupplyExpect histogram
+    for (int i = threadIdx.x; i < C; i += THREADS) {
+        const int lv = (int)icnt[i];
+        e.a[i] = lv; e.b[i] = lv;
+        if (e.tr) e.tr[C + i] = lv;
+        if (e.ob) e.ob[3 * C + i] = (uint16_t)lv;
+        sup[i] = 0u;
+    }
+}
+template <int THREADS>
+__device__ __noinline__ void nq_emit_supply(NqEmit e, const uint32_t *sup, int C)
+{   // SupplyExpect (:880-891)
+    for (int i = threadIdx.x; i < C; i += THREADS) {
+        const int sv = (int)sup[i];
+        e.a[i] = sv;
+        if (e.tr) e.tr[2 * C + i] = sv;
+        if (e.ob) e.ob[2 * C + i] = (uint16_t)sv;
+    }
 }
 
 template <int THREADS, int MINB, bool TIMEOUT>
@@ -231,7 +224,7 @@ rollout_nq_kernel(DevParams P, int k0, int nticks, int fresh)
     uint32_t *sup = reinterpret_cast<uint32_t *>(smraw + L.ooff);         // alias, live between the match and the next tick
     unsigned long long *acc = reinterpret_cast<unsigned long long *>(smraw + L.acc);
     uint32_t *misc = reinterpret_cast<uint32_t *>(smraw + L.misc);
-    // misc: [0..3] arrival-queue lengths, [4] overflow round stamp, [5] warp work list length, [6] lane work list length
+    // misc: [0..3] arrival-queue lengths, [4] overflow round stamp, [5] work list length, [7] work list cursor
     const int qcap = L.qcap / NQ_QUEUES;                                  // entries per arrival queue
     const uint32_t sm_sa = smem_addr(smraw);
     NqSm S;
@@ -312,36 +305,14 @@ rollout_nq_kernel(DevParams P, int k0, int nticks, int fresh)
     uint32_t round = 0;                             // arrival rounds so far (uniform): stamps the overflow flag
     __syncthreads();
 
-    // arrivals due by tick kk (arrive tick <= kk, en route): queue them, bucketed by node % 4, for the appending warps.
-    // Two u16 per 32-bit op: (0x8000 + kk) - (t & 0x7FFF) keeps bit 15 iff (t & 0x7FFF) <= kk and never borrows into the
-    // other half; idle (0xFFFF) and padding (0x7FFF) entries have 0x7FFF > kk.  With `count_supply` the order-carrying
-    // ones are also counted per destination cluster: SupplyExpectFunction (simulator.py:880-891) of tick kk - 1 is exactly
-    // "vehicles with an order that arrive by the start of the next slot".
-    auto scan_arrivals = [&](int kk, bool count_supply) {
-        const uint32_t k2 = ((uint32_t)kk | 0x8000u) * 0x00010001u;
-        for (int g = tid; g < ngroups; g += THREADS) {
-            const uint4 a = reinterpret_cast<const uint4 *>(arr)[g];
-            const uint32_t f0 = (k2 - (a.x & 0x7FFF7FFFu)) & 0x80008000u, f1 = (k2 - (a.y & 0x7FFF7FFFu)) & 0x80008000u;
-            const uint32_t f2 = (k2 - (a.z & 0x7FFF7FFFu)) & 0x80008000u, f3 = (k2 - (a.w & 0x7FFF7FFFu)) & 0x80008000u;
-            if (f0 | f1 | f2 | f3) {
-                // bit i: low half of word i (vehicle 2i), bit 16 + i: high half (vehicle 2i + 1)
-                uint32_t b = (f0 >> 15) | (f1 >> 14) | (f2 >> 13) | (f3 >> 12);
-                while (b) {
-                    const int p = __ffs(b) - 1; b &= b - 1;
-                    const uint32_t v = (uint32_t)(g * 8 + (p < 16 ? 2 * p : 2 * (p - 16) + 1));
-                    const uint32_t x = lds_u16(S.node + 2u * v);
-                    const uint32_t qi = x & (NQ_QUEUES - 1);
-                    const uint32_t pos = atoms_add(S.misc + 4u * qi, 1u);
-                    if (pos < (uint32_t)qcap) sts_u16(S.q + 2u * (qi * (uint32_t)qcap + pos), v);
-                    if (count_supply && (lds_u16(S.arr + 2u * v) & 0x8000u)) atomicAdd(&sup[n2c[x]], 1u);
-                }
-            }
-        }
-    };
-    scan_arrivals(k0, false);
-
-    for (int k = k0; k < k0 + nticks; k++) {
-        const bool emit = (k == k0 + nticks - 1) || P.trace != nullptr || P.obs != nullptr;
+    // (the arrival scan for tick k + 1 closes tick k; "tick" k0 - 1 stands for the state before the window)
+    for (int k = k0 - 1; k < k0 + nticks; k++) {
+      bool emit = false;
+      NqEmit em; em.a = em.b = nullptr; em.tr = nullptr; em.ob = nullptr;
+      if (k >= k0) {
+        emit = (k == k0 + nticks - 1) || P.trace != nullptr || P.obs != nullptr;
+        em.tr = P.trace ? P.trace + (((size_t)r * P.T + k) * 4) * C : nullptr;
+        em.ob = P.obs ? P.obs + ((size_t)r * P.obs_ring + (k % P.obs_ring)) * 4 * C : nullptr;
         const int tb = toff[k], n_tick = toff[k + 1] - tb;
         const uint16_t *coff = P.coff + ((size_t)ro * P.T + k) * (C + 1);
         // the tick's grouped orders are streamed from HBM exactly once: ask for them now (128-byte lines into L2), they
@@ -410,21 +381,12 @@ rollout_nq_kernel(DevParams P, int k0, int nticks, int fresh)
             }
             __syncthreads();
             if (misc[4] != round) break;
-            scan_arrivals(k, false);                                     // more arrivals than queue slots: next batch
+            nq_scan_arrivals<THREADS>(S.arr, S.node, S.misc, S.q, ngroups, qcap, k, nullptr, n2c);     // more arrivals than queue slots: next batch
         }
 
-        // ---- PerMatchIdleVehicles (simulator.py:909-910), len(Cluster.Orders)
         if (emit) {
-            int *g_pm = P.per_match + (size_t)r * C, *g_no = P.n_orders + (size_t)r * C;
-            for (int i = tid; i < C; i += THREADS) { g_pm[i] = (int)icnt[i]; g_no[i] = (int)ooff[i + 1] - (int)ooff[i]; }
-            if (P.trace) {
-                int *tr = P.trace + (((size_t)r * P.T + k) * 4) * C;
-                for (int i = tid; i < C; i += THREADS) { tr[i] = (int)icnt[i]; tr[3 * C + i] = (int)ooff[i + 1] - (int)ooff[i]; }
-            }
-            if (P.obs) {
-                uint16_t *ob = P.obs + ((size_t)r * P.obs_ring + (k % P.obs_ring)) * 4 * C;
-                for (int i = tid; i < C; i += THREADS) { ob[i] = (uint16_t)icnt[i]; ob[C + i] = (uint16_t)(ooff[i + 1] - ooff[i]); }
-            }
+            em.a = P.per_match + (size_t)r * C; em.b = P.n_orders + (size_t)r * C;
+            nq_emit_before_match<THREADS>(em, icnt, ooff, C);
         }
 
         // ---- MatchFunction, own cluster (simulator.py:921-934, 943-969)
@@ -435,16 +397,14 @@ rollout_nq_kernel(DevParams P, int k0, int nticks, int fresh)
         cm.arr_sa = S.arr; cm.node_sa = S.node; cm.key_sa = S.key; cm.g_loc = P.veh_loc + vb; cm.res = res_base + tb;
         cm.k = k; cm.magic = P.period_magic; cm.pm1 = P.period - 1;
         // -- classify: clusters with orders AND idle vehicles.  ONE idle vehicle (the most common case): without a
-        //    timeout the cluster's first order takes it, no argmin.  Idle vehicles on <= 4 nodes and <= 4 orders to serve:
-        //    back of the work list (one THREAD each); the others: front of the list (one WARP each).
+        //    timeout the cluster's first order takes it, no argmin.  The others go on the work list.
         for (int c_l = tid; c_l < C; c_l += THREADS) {
             const uint32_t o0 = lds_u16(S.ooff + 2u * (uint32_t)c_l), o1 = lds_u16(S.ooff + 2u * (uint32_t)c_l + 2u);
             const int m_l = (int)(o1 - o0);
             const int n_l = (int)lds_u32(S.icnt + 4u * (uint32_t)c_l);
             if (m_l > 0 && n_l > 0) {
-                const int off_c = cl_off[c_l];
-                const bool one_word = cl_off[c_l + 1] - off_c <= 32;
                 if (!TIMEOUT && n_l == 1) {
+                    const int off_c = cl_off[c_l];
                     int li = 0;
                     for (int ww = 0; ww < W; ww++) { const uint32_t o = occ[c_l * W + ww]; if (o) { li = 32 * ww + __ffs(o) - 1; occ[c_l * W + ww] = 0u; break; } }
                     const uint32_t x = cl_nodes[off_c + li];
@@ -458,126 +418,164 @@ rollout_nq_kernel(DevParams P, int k0, int nticks, int fresh)
                     t_match++; t_wait += wait; t_val += o_val; t_look++;
                     sts_u32(S.icnt + 4u * (uint32_t)c_l, 0u);
                 } else {
-                    // one THREAD can match it when <= 4 of its nodes hold idle vehicles and <= 4 orders can be served
-                    const bool lp = !TIMEOUT && one_word && min(m_l, n_l) <= 4 && __popc(occ[c_l * W]) <= 4;
-                    const uint32_t slot = lp ? (uint32_t)(C - 1) - atoms_add(S.misc + 24u, 1u) : atoms_add(S.misc + 20u, 1u);
+                    const uint32_t slot = atoms_add(S.misc + 20u, 1u);
                     sts_u16(S.wl + 2u * slot, (uint32_t)c_l);
                 }
             }
         }
         __syncthreads();
-        // -- one thread per small cluster (dense: no idle lanes between them)
-        if constexpr (!TIMEOUT) {
-            const int n_lp = (int)misc[6];
-            if (tid < n_lp) {
-                NqLaneArgs lq;
-                lq.key = S.key; lq.arr = S.arr; lq.node = S.node; lq.nxt = S.nxt; lq.tail = S.tail; lq.nodes_u = nodes_u;
-                lq.k = (uint32_t)k; lq.pm1 = (uint32_t)(P.period - 1); lq.magic = P.period_magic;
-                lq.spd_t = spd_t; lq.sidx_t = sidx_t; lq.cl_nodes = cl_nodes; lq.cost = cost; lq.g_loc = cm.g_loc; lq.res = cm.res;
-                for (int i = tid; i < n_lp; i += THREADS) {
-                    const uint32_t c_l = lds_u16(S.wl + 2u * (uint32_t)(C - 1 - i));
-                    const uint32_t o0 = lds_u16(S.ooff + 2u * c_l), o1 = lds_u16(S.ooff + 2u * c_l + 2u);
-                    const int n_l = (int)lds_u32(S.icnt + 4u * c_l);
-                    const uint4 st = nq_lane_match(lq, min((int)(o1 - o0), n_l), n_l, (int)o0, cl_off[c_l],
-                                                   S.occ + 4u * c_l * (uint32_t)W, S.icnt + 4u * c_l);
-                    t_match += st.x; t_wait += st.y; t_val += st.z; t_look += st.w;
-                }
-            }
-        }
-        // -- warps pop the other clusters off the work list: ONE LANE PER NODE of the cluster.  The winner of order j is
-        //    only RECORDED by the lane that holds that order (lane j % 32); the commits run lane-parallel once per 32 orders.
+        // -- the other clusters: warps take them off the work list in BATCHES.  The idle-vehicle nodes of the batch's
+        //    clusters are laid out over the 32 lanes (one lane = one node queue: tail, head, head's key in registers) and
+        //    so are the batch's orders (one lane = one order, for the commit); the cost bytes of the first 8 orders of
+        //    every cluster are gathered up front, 4 per register.  The sequential part -- order after order, cluster
+        //    after cluster: REDUX.MIN over the cost bytes, key REDUX on ties, pop -- then touches shared memory only,
+        //    and the whole batch is committed lane-parallel in one pass.  Two HBM/L2 round trips per batch (orders,
+        //    costs) instead of two per cluster.
         {
             const int n_work = (int)misc[5];
+            // narrow CTAs (4 warps) claim exactly the clusters of one batch with a compare-and-swap on the list cursor
+            // (best balance); wide CTAs reserve 8 work items at a time (32 warps retrying a CAS cost more than they gain)
+            constexpr bool RESERVE = NW > 4;
+            int resv = 0, resv_end = 0;                                          // this warp's reservation [resv, resv_end) of work items
             while (true) {
-                uint32_t slot = 0;
-                if (lane == 0) slot = atoms_add(S.misc + 28u, 1u);
-                slot = __shfl_sync(FULL, slot, 0);
-                if ((int)slot >= n_work) break;
-                const uint32_t c = lds_u16(S.wl + 2u * slot);
-                const uint32_t b0 = lds_u16(S.ooff + 2u * c);
-                const int m = (int)(lds_u16(S.ooff + 2u * c + 2u) - b0);
-                const int n = (int)lds_u32(S.icnt + 4u * c);
-                const int off_c = cl_off[c], nn = cl_off[c + 1] - off_c;
-                const int steps = TIMEOUT ? m : min(m, n);              // a timeout reject does not consume a vehicle
-                const uint32_t *spd_c = spd_t + b0;
-                const uint16_t *sidx_c = sidx_t + b0;
-                // lane l holds order (chunk base + l): pickup | delivery, index in the tick, RoadCost(pickup, delivery)
-                // (:341-342; gathered now, consumed by the deferred commit) and the row offset of its pickup
-                uint32_t pdv = 0, idxv = 0, oval = 0, rowv = 0;
-                if (lane < steps) {
-                    pdv = spd_c[lane]; idxv = sidx_c[lane];
-                    rowv = (pdv & 0xFFFFu) * nodes_u;
-                    oval = cost[(pdv >> 16) * nodes_u + (pdv & 0xFFFFu)];
+                if (RESERVE ? resv >= resv_end : true) {
+                    uint32_t cur = 0;
+                    if (lane == 0) cur = RESERVE ? atoms_add(S.misc + 28u, 8u) : lds_u32(S.misc + 28u);
+                    cur = __shfl_sync(FULL, cur, 0);
+                    if ((int)cur >= n_work) break;
+                    resv = (int)cur; resv_end = min(n_work, (int)cur + 8);
                 }
-                uint32_t my_ex = ROLL_DEAD, my_wait = 0;                // winner of THIS lane's order, committed by flush()
-                auto flush = [&]() {
-                    if (my_ex != ROLL_DEAD) {
-                        cm.commit(my_ex, my_wait, oval, pdv >> 16, idxv);
-                        t_match++; t_wait += my_wait; t_val += oval;
-                        my_ex = ROLL_DEAD;
+                const uint32_t cur = (uint32_t)resv;
+                // descriptors: lane b < 8 looks at work item cur + b
+                const bool have = lane < 8 && resv + lane < resv_end;
+                uint32_t c = 0, b0 = 0, occw = 0; int steps = 0, m = 0, n = 0, nocc = 0, off_c = 0, nn = 0;
+                if (have) {
+                    c = lds_u16(S.wl + 2u * (cur + (uint32_t)lane));
+                    b0 = lds_u16(S.ooff + 2u * c); m = (int)(lds_u16(S.ooff + 2u * c + 2u) - b0);
+                    n = (int)lds_u32(S.icnt + 4u * c);
+                    off_c = cl_off[c]; nn = cl_off[c + 1] - off_c;
+                    occw = lds_u32(S.occ + 4u * c * (uint32_t)W);
+                    steps = TIMEOUT ? m : min(m, n); nocc = __popc(occw);
+                }
+                const bool batchable = have && !TIMEOUT && nn <= 32 && steps <= 32;
+                int ns = batchable ? nocc : 64, os = batchable ? steps : 64;      // a cluster that cannot be batched ends the prefix
+#pragma unroll
+                for (int d = 1; d < 8; d <<= 1) {
+                    const int a1 = __shfl_up_sync(FULL, ns, d), a2 = __shfl_up_sync(FULL, os, d);
+                    if (lane >= d) { ns += a1; os += a2; }
+                }
+                const unsigned fm = __ballot_sync(FULL, batchable && ns <= 32 && os <= 32);
+                const int k = min(8, __ffs(~fm) - 1);                            // clusters in this batch (leading run)
+                if constexpr (RESERVE) resv += k ? k : 1;
+                else {
+                    uint32_t old = cur;
+                    if (lane == 0) old = atomicCAS(&misc[7], cur, cur + (uint32_t)(k ? k : 1));
+                    if (__shfl_sync(FULL, old, 0) != cur) continue;              // another warp moved the cursor: look again
+                }
+                uint32_t my_ex = ROLL_DEAD, my_wait = 0;                        // winner of THIS lane's order
+                if (k) {
+                    const int node_start = ns - nocc, ord_start = os - steps;   // (descriptor lanes)
+                    const int NS = __shfl_sync(FULL, ns, k - 1), OS = __shfl_sync(FULL, os, k - 1);
+                    // bit e set: a cluster of the batch ends right before slot e; cluster of slot l = #ends at or before l
+                    const unsigned Wn = __reduce_or_sync(FULL, (lane < k && ns < 32) ? 1u << ns : 0u);
+                    const unsigned Wo = __reduce_or_sync(FULL, (lane < k && os < 32) ? 1u << os : 0u);
+                    const unsigned upto = (2u << lane) - 1u;
+                    const int bn = min(__popc(Wn & upto), k - 1), bo = min(__popc(Wo & upto), k - 1);
+                    const bool is_node = lane < NS, is_ord = lane < OS;
+                    // ---- this lane as a NODE slot
+                    const uint32_t cn = __shfl_sync(FULL, c, bn), occn = __shfl_sync(FULL, occw, bn);
+                    const int offn = __shfl_sync(FULL, off_c, bn), i_n = lane - __shfl_sync(FULL, node_start, bn);
+                    const int my_os = __shfl_sync(FULL, ord_start, bn), my_steps = __shfl_sync(FULL, steps, bn);
+                    uint32_t x = 0, t = NQ_NONE, hv = NQ_NONE, hk = ROLL_DEAD, li = 0;
+                    bool alive = false;
+                    if (is_node) {
+                        li = __fns(occn, 0, i_n + 1);                            // the i-th node of the cluster that holds idle vehicles
+                        x = cl_nodes[offn + (int)li];
+                        t = lds_u16(S.tail + 2u * x); hv = lds_u16(S.nxt + 2u * t); hk = lds_u32(S.key + 4u * hv);
+                        alive = true;
                     }
-                };
-                int live = n;
-                if (nn <= 32) {
-                    // register-resident: lane l owns node l of the cluster (its queue's tail, head, the head's key)
-                    const uint32_t occ_sa = S.occ + 4u * c * (uint32_t)W;
-                    bool alive = (lds_u32(occ_sa) >> lane) & 1u;
-                    uint32_t x = 0, t = NQ_NONE, hv = NQ_NONE, hk = ROLL_DEAD;
-                    if (lane < nn) x = cl_nodes[off_c + lane];
-                    if (alive) { t = lds_u16(S.tail + 2u * x); hv = lds_u16(S.nxt + 2u * t); hk = lds_u32(S.key + 4u * hv); }
                     const uint32_t x16 = x << 16;
-                    const uint8_t *cx = cost + x;                            // RoadCost(node, pickup) = cost[pickup][node]
-                    for (int jb = 0; jb < steps; jb += 32) {
-                        if (jb) {                                            // next 32 orders of the cluster
-                            __syncwarp();
-                            flush();
-                            pdv = 0; idxv = 0; rowv = 0;
-                            if (jb + lane < steps) {
-                                pdv = spd_c[jb + lane]; idxv = sidx_c[jb + lane];
-                                rowv = (pdv & 0xFFFFu) * nodes_u;
-                                oval = cost[(pdv >> 16) * nodes_u + (pdv & 0xFFFFu)];
-                            }
+                    const uint8_t *cx = cost + x;                                // RoadCost(node, pickup) = cost[pickup][node]
+                    // ---- this lane as an ORDER slot: pickup | delivery, index in the tick, RoadCost(pickup, delivery)
+                    //      (:341-342, consumed by the commit) and the row offset of its pickup
+                    const uint32_t b0o = __shfl_sync(FULL, b0, bo);
+                    const int j_o = lane - __shfl_sync(FULL, ord_start, bo);
+                    uint32_t pdv = 0, idxv = 0, oval = 0, rowv = 0;
+                    if (is_ord) {
+                        pdv = spd_t[b0o + (uint32_t)j_o]; idxv = sidx_t[b0o + (uint32_t)j_o];
+                        rowv = (pdv & 0xFFFFu) * nodes_u;
+                        oval = cost[(pdv >> 16) * nodes_u + (pdv & 0xFFFFu)];
+                    }
+                    // cost bytes of orders [jb, jb + 8) of the lane's own cluster, for the lanes selected by `who`
+                    uint32_t cA = 0, cB = 0;
+                    auto gather8 = [&](int jb, bool who) {
+                        uint32_t v[8];
+#pragma unroll
+                        for (int jj = 0; jj < 8; jj++) {
+                            const uint32_t row = __shfl_sync(FULL, rowv, (my_os + jb + jj) & 31);
+                            v[jj] = ldg_u8_if(cx + row, who && alive && jb + jj < my_steps, 0u);
                         }
-                        const int cnt = min(32, steps - jb);
-                        // the cost byte depends on (pickup, node) only: gathers of later orders are issued before order j is
-                        // resolved and stay valid whatever vehicle the node's queue then leads with
-                        // three gathers in flight: orders j, j + 1, j + 2 (most clusters serve <= 3 orders: one round trip)
-                        uint32_t c0 = ldg_u8_if(cx + __shfl_sync(FULL, rowv, 0), alive, ROLL_DEAD);
-                        uint32_t c1 = ldg_u8_if(cx + __shfl_sync(FULL, rowv, 1), alive, ROLL_DEAD);
-                        uint32_t c2 = ldg_u8_if(cx + __shfl_sync(FULL, rowv, 2), alive, ROLL_DEAD);
-                        for (int j = 0; j < cnt; j++) {
-                            const uint32_t cst = c0;
-                            // (lanes past the chunk hold row 0: a valid address; wrapped lanes re-read rows that are not used)
-                            c0 = c1; c1 = c2;
-                            c2 = ldg_u8_if(cx + __shfl_sync(FULL, rowv, (j + 3) & 31), alive, ROLL_DEAD);
+                        if (who) {
+                            cA = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
+                            cB = v[4] | (v[5] << 8) | (v[6] << 16) | (v[7] << 24);
+                        }
+                    };
+                    gather8(0, is_node);
+                    // ---- the sequential part
+                    for (int b = 0; b < k; b++) {
+                        const int sb = __shfl_sync(FULL, steps, b), osb = __shfl_sync(FULL, ord_start, b);
+                        const bool mine = is_node && bn == b;
+                        for (int j = 0; j < sb; j++) {
+                            if ((j & 7) == 0 && j) gather8(j, mine);
+                            const uint32_t byte = (((j & 4) ? cB : cA) >> ((j & 3) * 8)) & 0xFFu;
+                            const uint32_t cst = (mine && alive) ? byte : ROLL_DEAD;
                             const uint32_t mn = __reduce_min_sync(FULL, cst);
-                            if constexpr (TIMEOUT) {
-                                if (lane == 0) t_look += (unsigned)live;
-                                if (mn == ROLL_DEAD) { j = cnt; jb = steps; continue; }      // no idle vehicle left: the rest stay "Reject"
-                                if (mn > thr32) continue;                    // TempMin[1] > PICKUPTIMEWINDOW (:943): stays "Reject"
-                            }
                             unsigned tied = __ballot_sync(FULL, cst == mn);
-                            if (tied & (tied - 1)) {                         // cost tie: first in IdleVehicles order wins (Q5)
+                            if (tied & (tied - 1)) {                             // cost tie: first in IdleVehicles order wins (Q5)
                                 const uint32_t kmin = __reduce_min_sync(FULL, cst == mn ? hk : ROLL_DEAD);
                                 tied = __ballot_sync(FULL, cst == mn && hk == kmin);
                             }
                             const int win = __ffs(tied) - 1;
                             const uint32_t wex = __shfl_sync(FULL, hv | x16, win);
-                            if (lane == j) { my_ex = wex; my_wait = mn; }
-                            if (lane == win) {                               // IdleVehicles.remove (:963)
+                            if (lane == osb + j) { my_ex = wex; my_wait = mn; }
+                            if (lane == win) {                                   // IdleVehicles.remove (:963)
                                 hv = nq_pop(x, t, hv, hk, S);
-                                if (hv == NQ_NONE) { alive = false; c0 = ROLL_DEAD; c1 = ROLL_DEAD; c2 = ROLL_DEAD; }
+                                if (hv == NQ_NONE) alive = false;
                             }
-                            live--;
                         }
                     }
+                    // ---- commit the batch, lane-parallel; per-cluster counters
+                    if (my_ex != ROLL_DEAD) {
+                        cm.commit(my_ex, my_wait, oval, pdv >> 16, idxv);
+                        t_match++; t_wait += my_wait; t_val += oval;
+                    }
+                    if (lane < k) {
+                        t_look += (unsigned)(steps * n - (steps * (steps - 1)) / 2);     // len(IdleVehicles) at every order
+                        sts_u32(S.icnt + 4u * c, (uint32_t)(n - steps));
+                        sts_u32(S.occ + 4u * c * (uint32_t)W, 0u);
+                    }
                     __syncwarp();
-                    flush();
-                    if constexpr (!TIMEOUT) { if (lane == 0) t_look += (unsigned)(steps * n - (steps * (steps - 1)) / 2); }
-                    const unsigned occ_new = __ballot_sync(FULL, alive);
-                    if (lane == 0) { sts_u32(occ_sa, occ_new); sts_u32(S.icnt + 4u * c, (uint32_t)live); }
-                } else {
-                    // clusters with more than 32 nodes: same scan, several nodes per lane, state read from shared memory
+                    if (is_node && alive) reds_or(S.occ + 4u * cn * (uint32_t)W, 1u << li);
+                    __syncwarp();
+                    continue;
+                }
+                // ---- one cluster on its own (more than 32 nodes or orders to serve, or a timeout threshold): several nodes
+                //      per lane, queue state read from shared memory
+                {
+                    c = __shfl_sync(FULL, c, 0); b0 = __shfl_sync(FULL, b0, 0); steps = __shfl_sync(FULL, steps, 0);
+                    n = __shfl_sync(FULL, n, 0); off_c = __shfl_sync(FULL, off_c, 0); nn = __shfl_sync(FULL, nn, 0);
+                    const uint32_t *spd_c = spd_t + b0;
+                    const uint16_t *sidx_c = sidx_t + b0;
+                    uint32_t pdv = 0, idxv = 0, oval = 0;
+                    if (lane < steps) { pdv = spd_c[lane]; idxv = sidx_c[lane]; oval = cost[(pdv >> 16) * nodes_u + (pdv & 0xFFFFu)]; }
+                    auto flush = [&]() {
+                        if (my_ex != ROLL_DEAD) {
+                            cm.commit(my_ex, my_wait, oval, pdv >> 16, idxv);
+                            t_match++; t_wait += my_wait; t_val += oval;
+                            my_ex = ROLL_DEAD;
+                        }
+                    };
+                    int live = n;
                     for (int j = 0; j < steps && live > 0; j++) {
                         if ((j & 31) == 0 && j > 0) {
                             __syncwarp();
@@ -600,7 +598,7 @@ rollout_nq_kernel(DevParams P, int k0, int nticks, int fresh)
                             }
                         }
                         const uint32_t mn = __reduce_min_sync(FULL, bc);
-                        if (mn > thr32) continue;
+                        if (mn > thr32) continue;                                // TempMin[1] > PICKUPTIMEWINDOW (:943): stays "Reject"
                         const uint32_t kmin = __reduce_min_sync(FULL, bc == mn ? bk : ROLL_DEAD);
                         const int win = __ffs(__ballot_sync(FULL, bc == mn && bk == kmin)) - 1;
                         uint32_t wex = 0;
@@ -632,34 +630,20 @@ rollout_nq_kernel(DevParams P, int k0, int nticks, int fresh)
         }
         __syncthreads();
 
-        // ---- after the match: PerDispatchIdleVehicles / LaterDispatchIdleVehicles (:1080-1087), next tick's arrival
-        //      queue and -- from the same scan -- SupplyExpect (:880-891) where it is observable
+        // ---- after the match: PerDispatchIdleVehicles / LaterDispatchIdleVehicles (:1080-1087)
         if (emit) {
-            int *g_pd = P.per_dispatch + (size_t)r * C, *g_lv = P.idle_live + (size_t)r * C;
-            int *tr = P.trace ? P.trace + (((size_t)r * P.T + k) * 4) * C : nullptr;
-            uint16_t *ob = P.obs ? P.obs + ((size_t)r * P.obs_ring + (k % P.obs_ring)) * 4 * C : nullptr;
-            for (int i = tid; i < C; i += THREADS) {
-                const int lv = (int)icnt[i];
-                g_pd[i] = lv; g_lv[i] = lv;
-                if (tr) tr[C + i] = lv;
-                if (ob) ob[3 * C + i] = (uint16_t)lv;
-                sup[i] = 0u;
-            }
+            em.a = P.per_dispatch + (size_t)r * C; em.b = P.idle_live + (size_t)r * C;
+            nq_emit_after_match<THREADS>(em, icnt, sup, C);
             __syncthreads();
         }
-        scan_arrivals(k + 1, emit);
-        if (emit) {
-            __syncthreads();
-            int *g_s = P.supply + (size_t)r * C;
-            int *tr = P.trace ? P.trace + (((size_t)r * P.T + k) * 4) * C : nullptr;
-            uint16_t *ob = P.obs ? P.obs + ((size_t)r * P.obs_ring + (k % P.obs_ring)) * 4 * C : nullptr;
-            for (int i = tid; i < C; i += THREADS) {
-                const int s = (int)sup[i];
-                g_s[i] = s;
-                if (tr) tr[2 * C + i] = s;
-                if (ob) ob[2 * C + i] = (uint16_t)s;
-            }
-        }
+      }
+      // ---- next tick's arrival queues and -- from the same scan -- SupplyExpect (:880-891) where it is observable
+      nq_scan_arrivals<THREADS>(S.arr, S.node, S.misc, S.q, ngroups, qcap, k + 1, emit ? sup : nullptr, n2c);
+      if (emit) {
+          __syncthreads();
+          em.a = P.supply + (size_t)r * C;
+          nq_emit_supply<THREADS>(em, sup, C);
+      }
     }
     __syncthreads();
 
