@@ -96,7 +96,7 @@ __host__ __device__ inline RollLayout roll_layout(int Vp, int C)
     L.icnt = o;   o += 4 * Cp;
     L.ioff = o;   o += 4 * (Cp + 4);
     L.wtot = o;   o += 4 * 40;
-    L.acc = o;    o += 8 * 8;
+    L.acc = o;    o += 8 * 10;                                  // window sums [0..6], arrival-queue length [7], orders / tick value [8..9]
     L.ooff = o;   o += 2 * (Cp + 8);
     L.wl_cnt = o; o += 16;
     L.wl_pd = o;  o += 4 * Cp;
@@ -350,7 +350,7 @@ rollout_local_kernel(DevParams P, int k0, int nticks, RollPolicy pol)
             tma_load_1d(sm_sa + (uint32_t)L.clus, P.veh_cluster + vb, b2, mbar_sa);
             tma_load_1d(key_sa0, P.veh_key + vb, 2u * b2, mbar_sa);
         }
-        if (tid < 8) acc[tid] = 0;
+        if (tid < 10) acc[tid] = 0;
         tma_mbar_wait(mbar_sa, 0);
         for (int g = tid; g < ngroups; g += THREADS) {
             U16x8 a, n, d; a.v = reinterpret_cast<uint4 *>(arrive)[g]; n.v = reinterpret_cast<uint4 *>(node)[g];
@@ -376,17 +376,16 @@ rollout_local_kernel(DevParams P, int k0, int nticks, RollPolicy pol)
             reinterpret_cast<uint4 *>(key)[2 * g] = g_key[2 * g];
             reinterpret_cast<uint4 *>(key)[2 * g + 1] = g_key[2 * g + 1];
         }
-        if (tid < 8) acc[tid] = 0;
+        if (tid < 10) acc[tid] = 0;
     }
-    // per-THREAD window accumulators, reduced once at window end
-    unsigned long long a_wait = 0, a_look = 0, a_val = 0, a_match = 0;
+    // window sums live in shared memory (acc[]): every warp adds its tick totals once per tick, so no accumulator
+    // registers are carried (and spilled) across the tick loop
     unsigned a_arrive = 0;
     const uint8_t *__restrict__ cost = P.cost;
     const uint16_t *__restrict__ n2c = P.n2c;
     const uint32_t nodes_u = (uint32_t)P.nodes;       // nodes <= 65535: pickup * nodes + loc fits 32 bits
     const bool no_timeout = P.threshold >= 255;       // cost bytes are <= 255: "cost > threshold" can never fire
     const uint32_t thr32 = P.threshold > 0xFFFFFFF0LL ? 0xFFFFFFF0u : (P.threshold < 0 ? 0u : (uint32_t)P.threshold);
-    long long a_orders = 0, a_tickval = 0;          // thread 0 only
     unsigned a_dnum = 0; unsigned long long a_dcost = 0;   // fused dispatch policy (POLICY)
     int last_moves = 0;
     __syncthreads();
@@ -791,8 +790,15 @@ rollout_local_kernel(DevParams P, int k0, int nticks, RollPolicy pol)
             __syncthreads();
         }
         }
-        a_match += t_match; a_val += t_val; a_wait += t_wait; a_look += t_look;
-        if (tid == 0) { a_orders += n_tick; a_tickval += P.tick_value[(size_t)ro * P.T + k]; }
+        {
+            const unsigned wm = __reduce_add_sync(FULL, t_match), ww_ = __reduce_add_sync(FULL, t_wait);
+            const unsigned wv = __reduce_add_sync(FULL, t_val), wk = __reduce_add_sync(FULL, t_look);
+            if (lane == 0 && wk) {
+                atomicAdd(&acc[0], (unsigned long long)wm); atomicAdd(&acc[1], (unsigned long long)ww_);
+                atomicAdd(&acc[2], (unsigned long long)wv); atomicAdd(&acc[3], (unsigned long long)wk);
+            }
+            if (tid == 0) { acc[8] += (unsigned long long)n_tick; acc[9] += (unsigned long long)P.tick_value[(size_t)ro * P.T + k]; }
+        }
         RPROF(8)
         __syncthreads();
         RPROF(9)
@@ -947,14 +953,6 @@ rollout_local_kernel(DevParams P, int k0, int nticks, RollPolicy pol)
                 g_key[2 * g + 1] = reinterpret_cast<uint4 *>(key)[2 * g + 1];
             }
         }
-        for (int d = 16; d; d >>= 1) {
-            a_match += __shfl_xor_sync(FULL, a_match, d); a_wait += __shfl_xor_sync(FULL, a_wait, d);
-            a_val += __shfl_xor_sync(FULL, a_val, d); a_look += __shfl_xor_sync(FULL, a_look, d);
-        }
-        if (lane == 0) {
-            atomicAdd(&acc[0], a_match); atomicAdd(&acc[1], a_wait);
-            atomicAdd(&acc[2], a_val); atomicAdd(&acc[3], a_look);
-        }
         const unsigned arr_w = __reduce_add_sync(FULL, a_arrive);
         if (lane == 0) atomicAdd(&acc[4], (unsigned long long)arr_w);
         if constexpr (POLICY) {
@@ -965,7 +963,7 @@ rollout_local_kernel(DevParams P, int k0, int nticks, RollPolicy pol)
         __syncthreads();
         if (tid == 0) {
             long long *st = P.stats + (size_t)r * VDS_NUM_STATS;
-            const long long matches = (long long)acc[0];
+            const long long matches = (long long)acc[0], a_orders = (long long)acc[8], a_tickval = (long long)acc[9];
             st[VDS_STAT_ORDER_NUM] += a_orders;
             st[VDS_STAT_REJECT_NUM] += a_orders - matches;              // every consumed order is matched or rejected
             st[VDS_STAT_SUM_ORDER_VALUE] += a_tickval - (long long)acc[2];   // value of the REJECTED orders (see stats_kernel)

@@ -829,7 +829,6 @@ gen_prepare_kernel(DevParams P, uint64_t seed, long long first_replica, int n_sl
     int *whist = wtot + 16;             // [GP_WARPS][Cp]
     uint32_t *pd_s = reinterpret_cast<uint32_t *>(whist + GP_WARPS * Cp);            // [maxOT] the tick's orders
     uint16_t *c_s = reinterpret_cast<uint16_t *>(pd_s + P.maxOT);                    // [maxOT] their pickup clusters
-    uint16_t *rk_s = c_s + ((P.maxOT + 1) & ~1);                                     // [maxOT] rank inside (warp segment, cluster)
     __shared__ long long s_val;
     const int k = blockIdx.x, r = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const unsigned long long g = (unsigned long long)(first_replica + r);
@@ -850,33 +849,18 @@ gen_prepare_kernel(DevParams P, uint64_t seed, long long first_replica, int n_sl
     int *mywh = whist + w * Cp;
     uint32_t *g_pd = order_pd + (size_t)r * P.Nmax + off;
     uint8_t *g_val = oval + (size_t)r * P.Nmax + off;
-    for (int base = s0; base < s1; base += 32) {
-        const int i = base + lane;
-        const bool valid = i < s1;
-        uint32_t pd = 0; int v = 0, c = 0;
-        if (valid) {
-            const Philox x = philox4x32_10((uint32_t)i, (uint32_t)s | (1u << 16), (uint32_t)g, (uint32_t)(g >> 32), (uint32_t)seed, (uint32_t)(seed >> 32));
-            const uint32_t pn = perm_pick[alias_draw(zipf_thr, zipf_alias, n_rank, x.c[0], x.c[1])];
-            const uint32_t dn = perm_drop[alias_draw(zipf_thr, zipf_alias, n_rank, x.c[2], x.c[3])];
-            pd = pn | (dn << 16);
-            v = P.cost[(size_t)dn * P.nodes + pn];                                    // RoadCost(pickup, delivery)
-            c = P.n2c[pn];
-            g_pd[i] = pd; g_val[i] = (uint8_t)v;
-            vs += v;
-        }
-        // stable rank of the order inside (this warp's segment, its cluster): orders are visited in index order
-        const bool cons = valid && i < n;
-        const unsigned cm = __ballot_sync(FULL, cons);
-        if (cons) {
-            vs_tick += v;
-            const unsigned peers = __match_any_sync(cm, c);
-            const int leader = __ffs(peers) - 1;
-            int start = 0;
-            if (lane == leader) { start = mywh[c]; mywh[c] = start + __popc(peers); }
-            start = __shfl_sync(peers, start, leader);
-            pd_s[i] = pd; c_s[i] = (uint16_t)c; rk_s[i] = (uint16_t)(start + __popc(peers & lanemask_lt()));
-        }
-        __syncwarp();
+    // (two independent order chains per thread in flight: the draw -> table reads -> cost gather chain is latency bound)
+#pragma unroll 2
+    for (int i = s0 + lane; i < s1; i += 32) {
+        const Philox x = philox4x32_10((uint32_t)i, (uint32_t)s | (1u << 16), (uint32_t)g, (uint32_t)(g >> 32), (uint32_t)seed, (uint32_t)(seed >> 32));
+        const uint32_t pn = perm_pick[alias_draw(zipf_thr, zipf_alias, n_rank, x.c[0], x.c[1])];
+        const uint32_t dn = perm_drop[alias_draw(zipf_thr, zipf_alias, n_rank, x.c[2], x.c[3])];
+        const uint32_t pd = pn | (dn << 16);
+        const int v = P.cost[(size_t)dn * P.nodes + pn];                              // RoadCost(pickup, delivery)
+        const int c = P.n2c[pn];
+        g_pd[i] = pd; g_val[i] = (uint8_t)v;
+        vs += v;
+        if (i < n) { vs_tick += v; pd_s[i] = pd; c_s[i] = (uint16_t)c; atomicAdd(&mywh[c], 1); }
     }
     __syncthreads();
     for (int c = tid; c < C; c += GP_THREADS) {
@@ -892,12 +876,23 @@ gen_prepare_kernel(DevParams P, uint64_t seed, long long first_replica, int n_sl
     const int tb = min(off, lim);                                                    // the clamped tick offset the rollout uses
     uint32_t *g_spd = spd + (size_t)r * P.Nmax + tb;
     uint16_t *g_sidx = sidx + (size_t)r * P.Nmax + tb;
-    // scatter: position = cluster offset + orders of the cluster in earlier warps' segments + rank inside the segment
-    for (int i = tid; i < n; i += GP_THREADS) {
-        const int c = c_s[i];
-        const int ww = min(i / max(seg, 1), GP_WARPS - 1);
-        const int pos = boff[c] + whist[ww * Cp + c] + rk_s[i];
-        g_spd[pos] = pd_s[i]; g_sidx[pos] = (uint16_t)i;
+    // stable scatter from the staged copy: whist[w][c] now holds the offset of warp w's segment inside cluster c
+    const int e1 = min(n, s1);
+    for (int base = s0; base < e1; base += 32) {
+        const int i = base + lane;
+        const bool valid = i < e1;
+        const unsigned vm = __ballot_sync(FULL, valid);
+        if (valid) {
+            const int c = c_s[i];
+            const unsigned peers = __match_any_sync(vm, c);
+            const int leader = __ffs(peers) - 1;
+            int start = 0;
+            if (lane == leader) { start = mywh[c]; mywh[c] = start + __popc(peers); }
+            start = __shfl_sync(peers, start, leader);
+            const int pos = boff[c] + start + __popc(peers & lanemask_lt());
+            g_spd[pos] = pd_s[i]; g_sidx[pos] = (uint16_t)i;
+        }
+        __syncwarp();
     }
     for (int d = 16; d; d >>= 1) { vs += __shfl_xor_sync(FULL, vs, d); vs_tick += __shfl_xor_sync(FULL, vs_tick, d); }
     if (lane == 0) { if (vs) atomicAddLL(vtotal + r, vs); if (vs_tick) atomicAddLL(&s_val, vs_tick); }
@@ -1644,7 +1639,7 @@ int vds_generate_prepared_orders(vds_handle h, uint64_t seed, int64_t first_repl
     cudaStream_t st = (cudaStream_t)stream;
     const DevParams &P = h->P;
     const int Cp = (P.C + 3) & ~3;
-    const size_t smem = sizeof(int) * (2 * Cp + 4 + 16 + GP_WARPS * Cp) + 4 * (size_t)P.maxOT + 4 * (size_t)((P.maxOT + 1) & ~1);
+    const size_t smem = sizeof(int) * (2 * Cp + 4 + 16 + GP_WARPS * Cp) + 4 * (size_t)P.maxOT + 2 * (size_t)((P.maxOT + 1) & ~1);
     if (smem > 200 * 1024) return fail(h, VDS_ERR_INVALID, "vds_generate_prepared_orders: max_orders_per_tick too large for one CTA");
     CK(cudaFuncSetAttribute(gen_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaMemsetAsync((void *)P.vtotal, 0, sizeof(int64_t) * P.OR, st));
