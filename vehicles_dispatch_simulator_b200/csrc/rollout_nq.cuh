@@ -27,7 +27,10 @@
 // Per tick and replica: 4 barriers (5 when the per-cluster observables are emitted), against 9-12 before.
 
 #define NQ_NONE 0xFFFFu
-#define NQ_QUEUES 4          // arrival queues per replica, bucketed by node % 4 and appended by warps 0..3 in parallel
+// arrival queues per replica, bucketed by node % Q and appended by warps 0..Q-1 in parallel: every warp of a CTA of up to
+// 32 warps (a CTA that owns a whole SM must not leave 28 of its warps waiting for four)
+#define NQ_QUEUES(NW) ((NW) >= 32 ? 32 : (NW) >= 16 ? 16 : (NW) >= 8 ? 8 : 4)
+#define NQ_QCNT 8            // misc[NQ_QCNT + q]: length of arrival queue q
 
 __device__ __forceinline__ uint32_t lds_u16(uint32_t a) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint32_t atoms_add(uint32_t a, uint32_t v) { uint32_t o; asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(o) : "r"(a), "r"(v) : "memory"); return o; }
@@ -35,8 +38,8 @@ __device__ __forceinline__ void reds_add(uint32_t a, uint32_t v) { asm volatile(
 __device__ __forceinline__ void reds_or(uint32_t a, uint32_t v) { asm volatile("red.shared.or.b32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void reds_and(uint32_t a, uint32_t v) { asm volatile("red.shared.and.b32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
 
-__host__ __device__ inline NqLayout nq_layout(int Vp, int C, int nodes_pad, int W)
-{
+__host__ __device__ inline NqLayout nq_layout(int Vp, int C, int nodes_pad, int W, bool wide)
+{   // wide: CTAs of more than 4 warps (up to 32 arrival queues: more counters, more queue entries)
     const int Cp = (C + 3) & ~3;
     NqLayout L;
     int o = 0;
@@ -52,14 +55,14 @@ __host__ __device__ inline NqLayout nq_layout(int Vp, int C, int nodes_pad, int 
     L.wl = o;    o += 2 * Cp;                                 // (u32[C]) of an emitting tick aliases them after the match
     L.wl2 = 0;
     o = (o + 3) & ~3;
-    // arrival queue entries (u16), split evenly over NQ_QUEUES; a tick with more arrivals takes extra rounds
+    // arrival queue entries (u16), split evenly over the queues; a tick with more arrivals takes extra rounds
     // (the Vp <= 2048 figure keeps a V = 2000 / 4139-node / 192-cluster replica at 32,208 B: 7 CTAs per SM need
     //  7 x (dynamic + 1 KB reserved), 256-byte granules, <= 228 KB, i.e. <= 32,256 B)
-    L.qcap = Vp <= 2048 ? 352 : ((Vp / 4 + 1023) & ~1023);
+    L.qcap = !wide ? 352 : max(1024, (Vp / 4 + 1023) & ~1023);
     L.q = o;     o += 2 * L.qcap;
     o = (o + 7) & ~7;
     L.acc = o;   o += 8 * 8;
-    L.misc = o;  o += 4 * 16;
+    L.misc = o;  o += 4 * (wide ? 48 : 16);                   // counters; wide CTAs have up to 32 arrival queues
     L.total = (o + 15) & ~15;
     return L;
 }
@@ -149,6 +152,7 @@ template <int THREADS>
 __device__ __noinline__ void nq_scan_arrivals(uint32_t arr_sa, uint32_t node_sa, uint32_t misc_sa, uint32_t q_sa, int ngroups,
                                               int qcap, int kk, uint32_t *sup, const uint16_t *__restrict__ n2c)
 {
+    constexpr uint32_t Q = NQ_QUEUES(THREADS / 32);
     const uint32_t k2 = ((uint32_t)kk | 0x8000u) * 0x00010001u;
     for (int g = threadIdx.x; g < ngroups; g += THREADS) {
         const uint4 a = lds_v4(arr_sa + 16u * (uint32_t)g);
@@ -161,8 +165,8 @@ __device__ __noinline__ void nq_scan_arrivals(uint32_t arr_sa, uint32_t node_sa,
                 const int p = __ffs(b) - 1; b &= b - 1;
                 const uint32_t v = (uint32_t)(g * 8 + (p < 16 ? 2 * p : 2 * (p - 16) + 1));
                 const uint32_t x = lds_u16(node_sa + 2u * v);
-                const uint32_t qi = x & (NQ_QUEUES - 1);
-                const uint32_t pos = atoms_add(misc_sa + 4u * qi, 1u);
+                const uint32_t qi = x & (Q - 1u);
+                const uint32_t pos = atoms_add(misc_sa + 4u * (NQ_QCNT + qi), 1u);
                 if (pos < (uint32_t)qcap) sts_u16(q_sa + 2u * (qi * (uint32_t)qcap + pos), v);
                 if (sup && (lds_u16(arr_sa + 2u * v) & 0x8000u)) atomicAdd(&sup[n2c[x]], 1u);
             }
@@ -224,8 +228,9 @@ rollout_nq_kernel(DevParams P, int k0, int nticks, int fresh)
     uint32_t *sup = reinterpret_cast<uint32_t *>(smraw + L.ooff);         // alias, live between the match and the next tick
     unsigned long long *acc = reinterpret_cast<unsigned long long *>(smraw + L.acc);
     uint32_t *misc = reinterpret_cast<uint32_t *>(smraw + L.misc);
-    // misc: [0..3] arrival-queue lengths, [4] overflow round stamp, [5] work list length, [7] work list cursor
-    const int qcap = L.qcap / NQ_QUEUES;                                  // entries per arrival queue
+    // misc: [4] overflow round stamp, [5] work list length, [7] work list cursor, [NQ_QCNT + q] length of arrival queue q
+    constexpr int NQQ = NQ_QUEUES(NW);
+    const int qcap = L.qcap / NQQ;                                        // entries per arrival queue
     const uint32_t sm_sa = smem_addr(smraw);
     NqSm S;
     S.key = sm_sa + (uint32_t)L.key; S.arr = sm_sa + (uint32_t)L.arr; S.node = sm_sa + (uint32_t)L.node;
@@ -274,18 +279,18 @@ rollout_nq_kernel(DevParams P, int k0, int nticks, int fresh)
         for (int i = tid; i < C; i += THREADS) icnt[i] = fresh ? 0u : (uint32_t)g_lv[i];
         for (int i = tid; i < C * W; i += THREADS) occ[i] = 0u;
         if (tid < 8) acc[tid] = 0;
-        if (tid < 16) misc[tid] = 0;
+        if (tid < NQ_QCNT + NQQ) misc[tid] = 0;
     }
     __syncthreads();
     if (fresh) {
         // straight after vds_reset: every vehicle idle, key = vehicle index (tick 0).  Warp q appends the vehicles
-        // standing on nodes == q (mod 4) in index order, so every queue comes out fully sorted.
-        if (w < NQ_QUEUES) {
+        // standing on nodes == q (mod #queues) in index order, so every queue comes out fully sorted.
+        if (w < NQQ) {
             for (int v0 = 0; v0 < P.V; v0 += 32) {
                 const int v = v0 + lane;
                 uint32_t x = 0;
                 bool active = v < P.V && (arr[v] & NQ_IDLE);
-                if (active) { x = node[v]; active = (x & (NQ_QUEUES - 1)) == (uint32_t)w; }
+                if (active) { x = node[v]; active = (x & (NQQ - 1)) == (uint32_t)w; }
                 if (active) {
                     const int c = n2c[x], li = node_local[x];
                     atomicAdd(&icnt[c], 1u); atomicOr(&occ[c * W + (li >> 5)], 1u << (li & 31));
@@ -336,8 +341,8 @@ rollout_nq_kernel(DevParams P, int k0, int nticks, int fresh)
         for (;;) {
             round++;
             __syncthreads();                                             // the arrival queues are complete; sup / ooff are free
-            if (w < NQ_QUEUES) {
-                const int q_total = (int)misc[w];
+            if (w < NQQ) {
+                const int q_total = (int)misc[NQ_QCNT + w];
                 const int n_arr = min(q_total, qcap);
                 const uint32_t q_sa = S.q + 2u * (uint32_t)(w * qcap);
                 for (int base = 0; base < n_arr; base += 32) {
@@ -361,7 +366,7 @@ rollout_nq_kernel(DevParams P, int k0, int nticks, int fresh)
                 if (lane == 0) {
                     if (n_arr) atomicAdd(&acc[4], (unsigned long long)n_arr);
                     if (q_total > qcap) misc[4] = round;
-                    misc[w] = 0u;
+                    misc[NQ_QCNT + w] = 0u;
                 }
             }
             if (first_round) {
@@ -434,16 +439,16 @@ rollout_nq_kernel(DevParams P, int k0, int nticks, int fresh)
         {
             const int n_work = (int)misc[5];
             // narrow CTAs (4 warps) claim exactly the clusters of one batch with a compare-and-swap on the list cursor
-            // (best balance); wide CTAs reserve 8 work items at a time (32 warps retrying a CAS cost more than they gain)
+            // (best balance); wide CTAs reserve 4 work items at a time (32 warps retrying a CAS cost more than they gain)
             constexpr bool RESERVE = NW > 4;
             int resv = 0, resv_end = 0;                                          // this warp's reservation [resv, resv_end) of work items
             while (true) {
                 if (RESERVE ? resv >= resv_end : true) {
                     uint32_t cur = 0;
-                    if (lane == 0) cur = RESERVE ? atoms_add(S.misc + 28u, 8u) : lds_u32(S.misc + 28u);
+                    if (lane == 0) cur = RESERVE ? atoms_add(S.misc + 28u, 4u) : lds_u32(S.misc + 28u);
                     cur = __shfl_sync(FULL, cur, 0);
                     if ((int)cur >= n_work) break;
-                    resv = (int)cur; resv_end = min(n_work, (int)cur + 8);
+                    resv = (int)cur; resv_end = min(n_work, (int)cur + (RESERVE ? 4 : 8));
                 }
                 const uint32_t cur = (uint32_t)resv;
                 // descriptors: lane b < 8 looks at work item cur + b

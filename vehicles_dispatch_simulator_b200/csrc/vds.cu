@@ -1220,15 +1220,23 @@ static int nq_configure(vds_handle h)
     h->nq_threads = 0;
     DevParams &P = h->P;
     if (!P.cl_off || !P.q_next || h->nq_off) return VDS_OK;
-    P.NQ = nq_layout(P.Vp, P.C, P.nodes_pad, P.W);
-    h->nq_smem = P.NQ.total;
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, h->cfg.device));
-    if (h->nq_smem > (int)prop.sharedMemPerBlockOptin) return VDS_OK;
-    const int per_sm = (int)prop.sharedMemPerMultiprocessor / (h->nq_smem + 1024);
-    h->nq_threads = per_sm >= 6 ? 128 : per_sm >= 3 ? 256 : per_sm >= 2 ? 512 : 1024;
-    { const char *e = getenv("VDS_NQ_THREADS");       // developer knob: force a CTA width
-      if (e && (atoi(e) == 128 || atoi(e) == 256 || atoi(e) == 512 || atoi(e) == 1024)) h->nq_threads = atoi(e); }
+    auto pick = [&](bool wide) {
+        P.NQ = nq_layout(P.Vp, P.C, P.nodes_pad, P.W, wide);
+        h->nq_smem = P.NQ.total;
+        if (h->nq_smem > (int)prop.sharedMemPerBlockOptin) return 0;
+        const int per_sm = (int)prop.sharedMemPerMultiprocessor / (((h->nq_smem + 255) & ~255) + 1024);
+        return per_sm >= 6 ? 128 : per_sm >= 3 ? 256 : per_sm >= 2 ? 512 : 1024;
+    };
+    h->nq_threads = pick(false);
+    if (h->nq_threads != 128) h->nq_threads = pick(true);          // CTAs of more than 4 warps use the wide layout
+    if (h->nq_threads == 0) return VDS_OK;
+    { const char *e = getenv("VDS_NQ_THREADS");       // developer knob: force a CTA width (the layout follows)
+      if (e && (atoi(e) == 128 || atoi(e) == 256 || atoi(e) == 512 || atoi(e) == 1024)) {
+          h->nq_threads = atoi(e);
+          P.NQ = nq_layout(P.Vp, P.C, P.nodes_pad, P.W, h->nq_threads != 128); h->nq_smem = P.NQ.total;
+      } }
     CK(cudaFuncSetAttribute(rollout_nq_kernel<128, 7, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->nq_smem));
     CK(cudaFuncSetAttribute(rollout_nq_kernel<256, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->nq_smem));
     CK(cudaFuncSetAttribute(rollout_nq_kernel<512, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->nq_smem));
