@@ -627,7 +627,7 @@ rollout_nq_kernel(DevParams P, int k0, int nticks, int fresh)
         {
             const unsigned wm = __reduce_add_sync(FULL, t_match), ww_ = __reduce_add_sync(FULL, t_wait);
             const unsigned wv = __reduce_add_sync(FULL, t_val), wk = __reduce_add_sync(FULL, t_look);
-            if (lane == 0 && wk) {
+            if (lane == 0 && (wm | wk)) {
                 atomicAdd(&acc[0], (unsigned long long)wm); atomicAdd(&acc[1], (unsigned long long)ww_);
                 atomicAdd(&acc[2], (unsigned long long)wv); atomicAdd(&acc[3], (unsigned long long)wk);
             }
