@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define VDS_ABI_VERSION 5
+#define VDS_ABI_VERSION 6
 
 typedef enum vds_status {
     VDS_OK = 0,
@@ -172,6 +172,50 @@ int  vds_padded_nodes(int nodes);
 int  vds_bind_cluster_nodes(vds_handle h, const int32_t *cl_node_off, const uint16_t *cl_nodes, const uint8_t *node_local,
                             int max_nodes_per_cluster);
 int  vds_bind_queues(vds_handle h, uint16_t *q_next, uint16_t *q_tail);
+
+/* ---- optional inputs of the node-mode neighbour search (csrc/search_nodes.cuh) -----------------------------
+ * The same observation as above, for MatchFunction with NeighborCanServer (simulator.py:921-940, 978-996): per
+ * replica and tick vds_update sorts the idle vehicles by (node, idle key) and vds_match keeps one byte per node --
+ * the number of idle vehicles still standing there -- in shared memory.  The candidates of an order are static, so
+ * they are sorted once per city: nodes are RANKED cluster by cluster (rank = position in the concatenation of
+ * Cluster.Nodes over cluster ids; any order inside a cluster) and for every pickup node p
+ *   own_list    u32[nodes][own_pitch]     the nodes n of p's cluster,
+ *   search_list u32[nodes][search_pitch]  the nodes n of the clusters at positions 1.. of the DFS pre-order search
+ *                                         list of p's cluster (FindServerVehicleFunction, :978-996),
+ * each row ascending in the packed word  RoadCost(n, p) << 24 | position << 16 | rank(n)  (position 0 in own_list)
+ * and padded with 0xFFFFFFFF to the pitch (a multiple of 32, with at least one full padding group of 32 at the end
+ * of the longest row).  The first entry of the row whose node is occupied is the reference's argmin; entries that
+ * agree in (cost, position) are resolved by the idle-list order.  Needs search lists of <= 255 clusters.
+ *   node_rank    u16[nodes]  node -> rank, 0xFFFF for a node outside every cluster
+ *   cluster_base i32[C+1]    first rank of every cluster
+ *   ranks_padded number of ranks rounded up to a multiple of 16
+ * and per-replica scratch the library fills every tick (contents meaningful only to the library):
+ *   node_count u8[R][ranks_padded], run_end u16[R][ranks_padded], node_count_exact u16[R][ranks_padded],
+ *   head_key u32[R][ranks_padded],
+ *   slot_vehicle u16[2][R][Vp], slot_key u32[2][R][Vp] (double-buffered: vds_update merges the previous tick's sorted
+ *   slots with this tick's arrivals; after vds_reset / vds_bind_state, a fused rollout window or a tick that does not
+ *   follow the previous update directly, it sorts from scratch.  A caller that writes the vehicle arrays itself must
+ *   call vds_bind_state again before the next vds_update).
+ * Once bound (and neighbour search on, shared memory sufficient, VDS_SEARCH_NODES != 0) vds_update / vds_match /
+ * vds_rollout use update_nodes_kernel + match_nodes_kernel; results are bit-identical to match_search_kernel. */
+typedef struct vds_search_nodes {
+    const uint16_t *node_rank;
+    const int32_t  *cluster_base;
+    const uint32_t *own_list;
+    const uint32_t *search_list;
+    uint8_t  *node_count;
+    uint16_t *run_end;
+    uint16_t *node_count_exact;
+    uint16_t *slot_vehicle;
+    uint32_t *slot_key;
+    uint32_t *head_key;
+    int32_t   ranks_padded;
+    int32_t   own_pitch;
+    int32_t   search_pitch;
+} vds_search_nodes;
+int  vds_bind_search_nodes(vds_handle h, const vds_search_nodes *s);
+/* 1 if vds_update / vds_match run the node-mode kernels for this handle */
+int  vds_search_nodes_active(vds_handle h);
 
 /* order_value[i] = cost_u8[delivery][pickup] and value_total, on device
  * (replaces the OrderValue pre-computation loop, simulator.py:341-342). */

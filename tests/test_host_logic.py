@@ -25,7 +25,7 @@ def test_c_abi_exports_every_declared_symbol():
     L = _native.lib()                      # loads libvds.so (no compute, no GPU needed)
     for name in declared:
         assert hasattr(L, name), name
-    assert L.vds_abi_version() == 5
+    assert L.vds_abi_version() == 6
     assert L.vds_padded_vehicles(2001) == 2008
     # struct layouts agree with the header's field counts
     assert ctypes.sizeof(_native.Config) == 12 * 4 + 8

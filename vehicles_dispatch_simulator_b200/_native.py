@@ -45,6 +45,12 @@ class Orders(C.Structure):
                                           "sorted_pd", "sorted_idx", "cluster_off", "tick_value")]
 
 
+class SearchNodes(C.Structure):
+    _fields_ = ([(n, C.c_void_p) for n in ("node_rank", "cluster_base", "own_list", "search_list", "node_count", "run_end",
+                                           "node_count_exact", "slot_vehicle", "slot_key", "head_key")]
+                + [("ranks_padded", C.c_int32), ("own_pitch", C.c_int32), ("search_pitch", C.c_int32)])
+
+
 STATE_FIELDS = ("veh_loc", "veh_cluster", "veh_arrive", "veh_dest", "veh_key", "order_res",
                 "per_match", "per_dispatch", "idle_live", "supply", "n_orders", "stats",
                 "idle_ent", "idle_off", "bucket_off", "bucket_ord", "disp_seq", "trace")
@@ -59,7 +65,8 @@ EXPORTS = ("vds_abi_version", "vds_padded_vehicles", "vds_create", "vds_destroy"
            "vds_bind_static", "vds_bind_orders", "vds_bind_state", "vds_compute_order_values",
            "vds_prepare_orders", "vds_reset", "vds_clear_results", "vds_update", "vds_match", "vds_supply_expect", "vds_dispatch", "vds_dispatch_strided", "vds_policy_random", "vds_rollout_policy_random", "vds_rollout", "vds_tick", "vds_rollout_is_fused", "vds_rollout_threads",
            "vds_stats", "vds_sync", "vds_launch_count", "vds_generate_orders", "vds_generate_prepared_orders", "vds_generate_placement",
-           "vds_rollout_kernel_name", "vds_padded_nodes", "vds_bind_cluster_nodes", "vds_bind_queues", "vds_bind_observations", "vds_observe", "vds_time_features", "vds_load_orders", "vds_cluster_cost_sums")
+           "vds_rollout_kernel_name", "vds_padded_nodes", "vds_bind_cluster_nodes", "vds_bind_queues", "vds_bind_observations", "vds_observe", "vds_time_features", "vds_load_orders", "vds_cluster_cost_sums",
+           "vds_bind_search_nodes", "vds_search_nodes_active")
 
 
 def build(force=False, verbose=False):
@@ -127,6 +134,8 @@ def lib():
         "vds_time_features": (C.c_int, [vp, i64, vp, vp, vp, vp, vp, vp, vp]),
         "vds_load_orders": (C.c_int, [vp, vp, vp, vp, i32, i32, vp, vp]),
         "vds_cluster_cost_sums": (C.c_int, [vp, vp, vp, vp, vp]),
+        "vds_bind_search_nodes": (C.c_int, [vp, C.POINTER(SearchNodes)]),
+        "vds_search_nodes_active": (C.c_int, [vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)

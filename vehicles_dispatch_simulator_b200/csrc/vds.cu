@@ -46,6 +46,12 @@ struct RollLayout {
 };
 // shared-memory layout of rollout_nq_kernel (rollout_nq.cuh)
 struct NqLayout { int key, arr, node, nxt, tail, icnt, occ, ooff, wl, wl2, q, acc, misc, total, qcap; };
+// node-mode neighbour search (search_nodes.cuh; vds_bind_search_nodes)
+struct SnParams {
+    const uint16_t *nrank; const int *cbase; const uint32_t *own_list, *search_list;
+    uint8_t *ncnt; uint16_t *runend, *gcnt, *sveh; uint32_t *skey, *hkey;
+    int NP, own_pitch, search_pitch;
+};
 struct DevParams {
     int R, V, Vp, C, nodes, Nmax, T, period, depth, ncs, OR, maxOT; unsigned period_magic;
     long long threshold;
@@ -61,7 +67,7 @@ struct DevParams {
     // node-queue rollout kernel: Cluster.Nodes as CSR + node -> index inside its cluster; persisted queue links
     const int *cl_off; const uint16_t *cl_nodes; const uint8_t *node_local; int W, nodes_pad;
     uint16_t *q_next, *q_tail;
-    RollLayout L; NqLayout NQ;
+    RollLayout L; NqLayout NQ; SnParams SN;
 };
 
 struct vds_handle_s {
@@ -73,6 +79,8 @@ struct vds_handle_s {
     int nq_state;                            // 0 stale (HBM queue links do not describe the vehicle table), 1 fresh reset, 2 valid
     bool nq_off;
     int n_sidx, n_ridx;                      // search-list sizes: decide the shared-memory staging of match_search_kernel
+    bool sn_bound, sn_off; int sn_smem, sn_tab_ints, sn_per_warp, sn_warps;   // node-mode neighbour search (search_nodes.cuh)
+    bool sn_valid; int sn_buf, sn_last_tick;       // the slot buffer `sn_buf` holds update(sn_last_tick)'s sorted idle vehicles
     char err[512];
     int64_t launches;
     int sm_count;
@@ -731,6 +739,7 @@ struct RollPolicy {
 
 #include "rollout.cuh"
 #include "rollout_nq.cuh"
+#include "search_nodes.cuh"
 
 // ------------------------------------------- synthetic Didi-shaped generator
 // smallest j with u < cdf[j]  (cdf non-decreasing, cdf[n-1] == 0xFFFFFFFF catches everything)
@@ -1136,6 +1145,7 @@ int vds_create(const vds_config *cfg, vds_handle *out)
     CK(cudaFuncSetAttribute(prepare_orders_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, prep_smem));
     { const char *e = getenv("VDS_FUSED_SEARCH"); h->fused_search = e && e[0] == '1'; }
     { const char *e = getenv("VDS_NO_NQ"); h->nq_off = e && e[0] == '1'; }
+    { const char *e = getenv("VDS_SEARCH_NODES"); h->sn_off = e && e[0] == '0'; }
     { const char *e = getenv("VDS_TMA"); P.tma = e ? (e[0] == '1') : VDS_TMA_DEFAULT; }
     P.nodes_pad = vds_padded_nodes(cfg->nodes);
     CK(cudaFuncSetAttribute(match_search_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -1210,7 +1220,7 @@ int vds_bind_state(vds_handle h, const vds_state *s)
     P.idle_live = s->idle_live; P.supply = s->supply; P.n_orders = s->n_orders; P.stats = (long long *)s->stats;
     P.idle_ent = (uint2 *)s->idle_ent; P.idle_off = s->idle_off; P.bucket_off = s->bucket_off;
     P.bucket_ord = s->bucket_ord; P.disp_seq = s->disp_seq; P.trace = s->trace;
-    h->have_state = true; return VDS_OK;
+    h->have_state = true; h->sn_valid = false; return VDS_OK;
 }
 
 // The node-queue kernel needs (a) Cluster.Nodes and (b) per-replica queue links in HBM.  Both optional: without
@@ -1270,6 +1280,47 @@ int vds_bind_queues(vds_handle h, uint16_t *q_next, uint16_t *q_tail)
 
 int vds_padded_nodes(int nodes) { return (nodes + 7) & ~7; }
 
+static bool sn_usable(vds_handle h) { return h->sn_bound && !h->sn_off && !local_mode(h) && h->sn_smem > 0; }
+
+int vds_bind_search_nodes(vds_handle h, const vds_search_nodes *s)
+{
+    if (!h || !s) return fail(h, VDS_ERR_INVALID, "vds_bind_search_nodes: null");
+    const void *ptrs[] = { s->node_rank, s->cluster_base, s->own_list, s->search_list, s->node_count, s->run_end,
+                           s->node_count_exact, s->slot_vehicle, s->slot_key, s->head_key };
+    for (const void *p : ptrs) if (!p) return fail(h, VDS_ERR_INVALID, "vds_bind_search_nodes: null pointer");
+    if (((uintptr_t)s->node_count | (uintptr_t)s->run_end) & 15)
+        return fail(h, VDS_ERR_INVALID, "vds_bind_search_nodes: node_count / run_end must be 16-byte aligned");
+    if (s->ranks_padded < 16 || (s->ranks_padded & 15) || s->ranks_padded > 65520 || s->own_pitch < 32 || (s->own_pitch & 31) ||
+        s->search_pitch < 32 || (s->search_pitch & 31))
+        return fail(h, VDS_ERR_INVALID, "vds_bind_search_nodes: ranks_padded must be a multiple of 16 (<= 65520), "
+                                        "own_pitch / search_pitch multiples of 32");
+    if (!h->have_static) return fail(h, VDS_ERR_UNBOUND, "vds_bind_search_nodes: vds_bind_static first");
+    SnParams &S = h->P.SN;
+    S.nrank = s->node_rank; S.cbase = s->cluster_base; S.own_list = s->own_list; S.search_list = s->search_list;
+    S.ncnt = s->node_count; S.runend = s->run_end; S.gcnt = s->node_count_exact; S.sveh = s->slot_vehicle; S.skey = s->slot_key; S.hkey = s->head_key;
+    S.NP = s->ranks_padded; S.own_pitch = s->own_pitch; S.search_pitch = s->search_pitch;
+    h->sn_bound = true; h->sn_smem = 0; h->sn_valid = false;
+    if (local_mode(h) || h->n_sidx < 0) return VDS_OK;            // own-cluster match: nothing to configure
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, h->cfg.device));
+    const int upd = sn_update_smem(h->P.C, S.NP, h->P.Vp);
+    if (upd > (int)prop.sharedMemPerBlockOptin) return VDS_OK;
+    for (int warps = MN_MAX_WARPS; warps >= 1; warps = warps > 7 ? 7 : warps - 1) {
+        const SnLayout L = sn_layout(h->P.C, S.NP, h->n_sidx, warps);
+        const int per_sm = (MN_MAX_WARPS / warps) < 2 ? 2 : (MN_MAX_WARPS / warps);      // CTAs that should share an SM
+        if (L.total > (int)prop.sharedMemPerBlockOptin) continue;
+        if (warps > 1 && (size_t)per_sm * (L.total + 1024) > prop.sharedMemPerMultiprocessor) continue;
+        h->sn_smem = L.total; h->sn_tab_ints = L.tab_ints; h->sn_per_warp = L.per_warp; h->sn_warps = warps;
+        break;
+    }
+    if (h->sn_smem > 0) {
+        CK(cudaFuncSetAttribute(match_nodes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->sn_smem));
+        CK(cudaFuncSetAttribute(update_nodes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, upd));
+    }
+    return VDS_OK;
+}
+int vds_search_nodes_active(vds_handle h) { return h && sn_usable(h); }
+
 static int ready(vds_handle h, bool need_orders)
 {
     if (!h) return VDS_ERR_INVALID;
@@ -1325,6 +1376,7 @@ int vds_reset(vds_handle h, const uint16_t *veh_loc0, void *stream)
     reset_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(P, veh_loc0);
     CKL("reset_kernel");
     h->nq_state = 1;                       // every vehicle idle, keys = vehicle index: queues are built from scratch
+    h->sn_valid = false;
     return VDS_OK;
 }
 
@@ -1340,6 +1392,17 @@ int vds_update(vds_handle h, int tick, void *stream)
     int rc = ready(h, true); if (rc) return rc;
     if (tick < 0 || tick >= h->P.T) return fail(h, VDS_ERR_INVALID, "vds_update: tick out of range");
     const int Cp = (h->P.C + 3) & ~3;
+    if (sn_usable(h)) {                    // neighbour search on per-node queues: idle vehicles sorted by (node, idle key)
+        // stable merge with the previous tick's sorted slots when they are still valid, from scratch otherwise
+        const int incremental = h->sn_valid && tick == h->sn_last_tick + 1;
+        h->sn_buf ^= 1;
+        update_nodes_kernel<<<h->P.R, UPD_THREADS, sn_update_smem(h->P.C, h->P.SN.NP, h->P.Vp), (cudaStream_t)stream>>>(
+            h->P, tick, incremental, h->sn_buf);
+        CKL("update_nodes_kernel");
+        h->sn_valid = true; h->sn_last_tick = tick;
+        h->nq_state = 0;
+        return VDS_OK;
+    }
     const int smem = (int)sizeof(int) * (4 * Cp + 8 + 16 + UPD_WARPS * Cp);
     update_kernel<<<h->P.R, UPD_THREADS, smem, (cudaStream_t)stream>>>(h->P, tick, local_mode(h) ? 1 : 0);
     CKL("update_kernel");
@@ -1357,6 +1420,13 @@ int vds_match(vds_handle h, int tick, void *stream)
         dim3 grid((P.C + 3) / 4, P.R);
         match_local_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(P, tick);
         CKL("match_local_kernel");
+    } else if (sn_usable(h)) {
+        if (!h->sn_valid || h->sn_last_tick != tick)
+            return fail(h, VDS_ERR_INVALID, "vds_match: vds_update of the same tick must precede it (node-mode neighbour search)");
+        const int wp = h->sn_warps, grid = (P.R + wp - 1) / wp;
+        cudaStream_t st = (cudaStream_t)stream;
+        match_nodes_kernel<<<grid, wp * 32, h->sn_smem, st>>>(P, tick, h->n_sidx, h->sn_tab_ints, h->sn_per_warp, h->sn_buf);
+        CKL("match_nodes_kernel");
     } else {
         const int per_cta = MS_WARPS * (3 * P.C + 2 + 96);
         const int tab = 2 * (P.C + 1) + ((h->n_sidx + 1) >> 1) + ((h->n_ridx + 1) >> 1);
@@ -1465,6 +1535,7 @@ int vds_rollout(vds_handle h, int tick0, int nticks, void *stream)
     }
     h->nq_state = 0;
     if (vds_rollout_is_fused(h)) {
+        h->sn_valid = false;
         cudaStream_t st = (cudaStream_t)stream;
         if (local_mode(h)) {
             switch (h->roll_threads) {

@@ -93,6 +93,54 @@ class City:
     def valid_nodes(self):
         return np.nonzero(self.node2cluster >= 0)[0].astype(np.uint16)
 
+    def search_node_tables(self, max_bytes=2 << 30):
+        """Static tables of the node-mode neighbour search (include/vds.h, vds_search_nodes): nodes ranked cluster by
+        cluster, and per pickup node the candidate nodes of its own cluster / of the rest of its DFS pre-order
+        search list as packed words cost << 24 | position << 16 | rank in ascending order (0xFFFFFFFF padding).
+        None when the search lists are too long for the packing or the tables would exceed max_bytes."""
+        if getattr(self, "_sn_tables", None) is not None:
+            return self._sn_tables
+        C = self.n_clusters
+        nodes = self.cluster_nodes if self.cluster_nodes is not None else \
+            [np.nonzero(self.node2cluster == c)[0] for c in range(C)]
+        nodes = [np.asarray(n, np.int64) for n in nodes]
+        order = np.concatenate(nodes) if len(nodes) else np.zeros(0, np.int64)          # rank -> node
+        soff, sidx = self.search_lists()
+        if len(order) == 0 or len(order) > 65520 or int(np.diff(soff).max()) > 255:
+            return None
+        cbase = np.cumsum([0] + [len(n) for n in nodes]).astype(np.int64)
+        rank = np.full(self.n_nodes, 0xFFFF, np.uint16)
+        rank[order] = np.arange(len(order), dtype=np.uint16)
+        own_len = max(len(n) for n in nodes)
+        reg_len = 0
+        for c in range(C):
+            reg_len = max(reg_len, int(sum(len(nodes[int(s)]) for s in sidx[soff[c] + 1:soff[c + 1]])))
+        own_pitch = ((own_len + 31) // 32 + 1) * 32
+        reg_pitch = ((reg_len + 31) // 32 + 1) * 32
+        if 4 * self.n_nodes * (own_pitch + reg_pitch) > max_bytes:
+            return None
+        own = np.full((self.n_nodes, own_pitch), 0xFFFFFFFF, np.uint32)
+        reg = np.full((self.n_nodes, reg_pitch), 0xFFFFFFFF, np.uint32)
+        for c in range(C):
+            pk = nodes[c]                                                                # the pickups of this cluster
+            if len(pk) == 0:
+                continue
+            r0 = np.arange(cbase[c], cbase[c + 1], dtype=np.uint32)
+            # cost_u8[end, start]: RoadCost(vehicle node n, pickup p) = cost_u8[p, n]
+            w = (self.cost_u8[np.ix_(pk, nodes[c])].astype(np.uint32) << 24) | r0[None, :]
+            own[pk, :len(r0)] = np.sort(w, axis=1)
+            lst = [int(s) for s in sidx[soff[c] + 1:soff[c + 1]]]
+            if lst:
+                rn = np.concatenate([nodes[s] for s in lst])
+                if len(rn):
+                    rr = np.concatenate([np.arange(cbase[s], cbase[s + 1], dtype=np.uint32) for s in lst])
+                    pos = np.concatenate([np.full(len(nodes[s]), t + 1, np.uint32) for t, s in enumerate(lst)])
+                    w = (self.cost_u8[np.ix_(pk, rn)].astype(np.uint32) << 24) | (pos << 16)[None, :] | rr[None, :]
+                    reg[pk, :len(rn)] = np.sort(w, axis=1)
+        self._sn_tables = dict(node_rank=rank, cluster_base=cbase.astype(np.int32), own_list=own, search_list=reg,
+                               ranks_padded=(len(order) + 15) & ~15)
+        return self._sn_tables
+
 
 def tick_offsets(order_minute, period):
     """tick(o) = floor(minute/p) + 1; tick 0 is empty; T = floor(m_last/p) + 5
@@ -187,6 +235,10 @@ class DispatchEngine:
                           + [self.trace.data_ptr() if trace else None]))
             self._ck(self.L.vds_bind_state(self.h, C.byref(s)))
             self._stats_out = z((R, N.VDS_NUM_STATS), torch.int64)
+            # ---- node-mode neighbour search (csrc/search_nodes.cuh): nodes ranked cluster by cluster, the cost table
+            #      with its columns in rank order, per-replica scratch of the per-node idle queues
+            if city.neighbor_can_server and city.depth_limit > 0:
+                self._bind_search_nodes()
             # ---- optional inputs of the node-queue rollout kernel (csrc/rollout_nq.cuh): Cluster.Nodes + per-replica
             #      queue links.  Opt-in (node_queues=True or VDS_NQ=1): bit-identical, but on the measured workloads the
             #      per-cluster slot-list kernel is still the faster one (profiles/r2_nq_*.md)
@@ -205,6 +257,32 @@ class DispatchEngine:
                     self.q_next = z((R, Vp), torch.uint16)
                     self.q_tail = z((R, self.L.vds_padded_nodes(city.n_nodes)), torch.uint16)
                     self._ck(self.L.vds_bind_queues(self.h, _ptr(self.q_next), _ptr(self.q_tail)))
+
+    def _bind_search_nodes(self):
+        """Static candidate tables + per-replica scratch of the node-mode neighbour search (include/vds.h,
+        vds_search_nodes).  The candidates of an order depend only on its pickup node, so they are sorted here, once."""
+        city, dev, R = self.city, self.device, self.R
+        tabs = city.search_node_tables()
+        if tabs is None:
+            return
+        z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dev)
+        NP = tabs["ranks_padded"]
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        self.sn = dict(node_rank=t(tabs["node_rank"]), cluster_base=t(tabs["cluster_base"]),
+                       own_list=t(tabs["own_list"]), search_list=t(tabs["search_list"]),
+                       node_count=z((R, NP), torch.uint8), run_end=z((R, NP), torch.uint16),
+                       node_count_exact=z((R, NP), torch.uint16),
+                       slot_vehicle=z((2, R, self.Vp), torch.uint16), slot_key=z((2, R, self.Vp), torch.uint32),
+                       head_key=z((R, NP), torch.uint32))
+        f = N.SearchNodes(*[self.sn[n].data_ptr() for n in ("node_rank", "cluster_base", "own_list", "search_list",
+                                                             "node_count", "run_end", "node_count_exact", "slot_vehicle",
+                                                             "slot_key", "head_key")],
+                          NP, tabs["own_list"].shape[1], tabs["search_list"].shape[1])
+        self._ck(self.L.vds_bind_search_nodes(self.h, C.byref(f)))
+
+    @property
+    def search_nodes_active(self):
+        return bool(self.L.vds_search_nodes_active(self.h))
 
     # ------------------------------------------------------------- plumbing
     def _ck(self, rc):
