@@ -21,7 +21,9 @@
 //       cost << 24 | position << 16 | node rank (vds_search_nodes.own_list / search_list).  An order reads 32
 //       consecutive words (one coalesced L2 load), gathers the 32 occupancy bytes from shared memory, and the
 //       first occupied entry is the reference's argmin (:928-933, 986-991); it moves on to the next 32 only when
-//       none of them is occupied.  No HBM round trip of replica state sits on the order-to-order chain: a pop is a
+//       none of them is occupied.  Because the lists are static, the first groups of the NEXT TWO orders are
+//       copied into a shared-memory ring with cp.async while the current order is resolved, so their L2
+//       latency is off the order-to-order chain.  No HBM round trip of replica state sits on the order-to-order chain: a pop is a
 //       byte decrement, the vehicle behind (node, ordinal) is looked up lane-parallel once per 32 orders
 //       (runend - ordinal -> sveh).  Only when several occupied nodes share the winning (cost, position) are the
 //       heads' idle keys read (runend -> skey) to apply the list order (Q5).
@@ -31,11 +33,15 @@
 
 struct SnLayout { int tab_ints, per_warp, total; };
 
+#define SN_OWN_CH 2            // 32-entry groups of the own-cluster list / of the search list requested ahead per order
+#define SN_REG_CH 4
+#define SN_RING 3              // orders in flight: the current one and the next two
+#define SN_SLOT_WORDS ((SN_OWN_CH + SN_REG_CH) * 32)
 static SnLayout sn_layout(int C, int NP, int n_sidx, int warps)
 {
     SnLayout L;
-    L.tab_ints = ((C + 1) + ((n_sidx + 1) >> 1) + 3) & ~3;
-    L.per_warp = (NP + 2 * C + 15) & ~15;                        // cnt u8[NP], live u16[C]
+    L.tab_ints = ((C + 1) + ((n_sidx + 1) >> 1) + C * ((C + 31) >> 5) + 3) & ~3;   // soff, sidx, search-list membership bitmaps
+    L.per_warp = (NP + 2 * C + 4 * SN_RING * SN_SLOT_WORDS + 15) & ~15;   // cnt u8[NP], live u16[C], candidate ring
     L.total = L.tab_ints * 4 + warps * L.per_warp;
     return L;
 }
@@ -295,22 +301,35 @@ update_nodes_kernel(DevParams P, int k, int incremental, int nbuf)
 }
 
 // -------------------------------------------------------------------------------------------- match (node mode)
+__device__ __forceinline__ void sn_cp_async4(void *smem_dst, const void *gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void sn_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void sn_cp_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
 #define MN_MAX_WARPS 14
 __global__ void __launch_bounds__(MN_MAX_WARPS * 32, 2)
-match_nodes_kernel(DevParams P, int k, int n_sidx, int tab_ints, int per_warp, int nbuf)
+match_nodes_kernel(DevParams P, int k, int n_sidx, int tab_ints, int per_warp, int nbuf, int dbg)
 {
     extern __shared__ int sm[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int C = P.C, NP = P.SN.NP;
+    const int C = P.C, NP = P.SN.NP, RW = (C + 31) >> 5;
     int *soff = sm;
     uint16_t *sidx = reinterpret_cast<uint16_t *>(soff + (C + 1));
+    unsigned *regmask = reinterpret_cast<unsigned *>(soff + (C + 1) + ((n_sidx + 1) >> 1));   // [C][RW] bit s of row c: s is in c's search list at a position >= 1
     for (int i = threadIdx.x; i <= C; i += blockDim.x) soff[i] = P.soff[i];
     for (int i = threadIdx.x; i < n_sidx; i += blockDim.x) sidx[i] = P.sidx[i];
+    for (int i = threadIdx.x; i < C * RW; i += blockDim.x) regmask[i] = 0;
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x)
+        for (int q = soff[c] + 1; q < soff[c + 1]; q++) { const int x = sidx[q]; regmask[c * RW + (x >> 5)] |= 1u << (x & 31); }
     __syncthreads();
     const int r = blockIdx.x * (blockDim.x >> 5) + w;
     if (r >= P.R) return;
     uint8_t *cnt = reinterpret_cast<uint8_t *>(sm + tab_ints) + (size_t)w * per_warp;    // [NP] idle vehicles standing on the node
     uint16_t *live = reinterpret_cast<uint16_t *>(cnt + NP);                             // [C] len(IdleVehicles)
+    uint32_t *ring = reinterpret_cast<uint32_t *>(cnt + NP + 2 * C + ((4 - ((NP + 2 * C) & 3)) & 3));   // [SN_RING][SN_SLOT_WORDS]
     const uint8_t *cnt0 = keep(P.SN.ncnt + (size_t)r * NP);                              // the same counts at the start of the tick
     {
         const uint4 *g = reinterpret_cast<const uint4 *>(cnt0);
@@ -334,6 +353,7 @@ match_nodes_kernel(DevParams P, int k, int n_sidx, int tab_ints, int per_warp, i
     const uint16_t *sveh = P.SN.sveh + (size_t)nbuf * P.R * P.Vp + vb;
     const uint32_t *ownl = keep(P.SN.own_list), *regl = keep(P.SN.search_list);
     const uint32_t own_pitch = (uint32_t)P.SN.own_pitch, reg_pitch = (uint32_t)P.SN.search_pitch;
+    const int own_pf = min(SN_OWN_CH, (int)(own_pitch >> 5)), reg_pf = min(SN_REG_CH, (int)(reg_pitch >> 5));
     const uint32_t thr = P.threshold > 255 ? 255u : (P.threshold < 0 ? 0u : (uint32_t)P.threshold);
     const bool never = P.threshold < 0;
 
@@ -349,69 +369,88 @@ match_nodes_kernel(DevParams P, int k, int n_sidx, int tab_ints, int per_warp, i
         return skey[(unsigned)runend[node] - c];
     };
 
+    uint32_t pdn = 0; int valn = 0;                              // the next 32 orders, requested one chunk ahead
+    if (lane < n) { pdn = opd[lane]; valn = oval[lane]; }
     for (int base = 0; base < n; base += 32) {
-        uint32_t pd = 0; int val = 0, oc = 0;
+        const uint32_t pd = pdn; const int val = valn;
+        if (base + 32 + lane < n) { pdn = opd[base + 32 + lane]; valn = oval[base + 32 + lane]; }
         const int nb_ord = min(32, n - base);
-        // an order with no idle vehicle anywhere in its search list is rejected now and for the rest of the tick
-        // (idle sets only shrink inside a tick): every lane classifies its own order, all of those are settled at once
-        bool dead_l = false;
+        // Every lane classifies its own order: S = idle vehicles in the rest of its search list.  An order with none
+        // there and none in its own cluster is rejected now and for the rest of the tick (idle sets only shrink
+        // inside a tick); all of those are settled at once.
+        int oc = 0, S = 0; bool dead_l = false;
+        const unsigned *myreg = regmask;
         if (lane < nb_ord) {
-            pd = opd[base + lane]; val = oval[base + lane]; oc = P.n2c[pd & 0xFFFF];
-            int any = live[oc];
-            if (!any) for (int q = soff[oc] + 1; q < soff[oc + 1]; q++) any |= live[sidx[q]];
-            dead_l = any == 0;
+            oc = __ldg(P.n2c + (pd & 0xFFFF));
+            for (int q = soff[oc] + 1; q < soff[oc + 1]; q++) S += live[sidx[q]];
+            dead_l = S == 0 && live[oc] == 0;
+            myreg = regmask + oc * RW;
         }
         unsigned todo = __ballot_sync(FULL, lane < nb_ord && !dead_l);
         rej += __popc(__ballot_sync(FULL, dead_l)); rejval += __reduce_add_sync(FULL, dead_l ? val : 0);
         uint32_t my_node = DEAD32, my_ord = 0, my_mn = 0;       // outcome of order base + lane ("Reject" until matched)
-        // The candidate lists are static, so the first entries of the NEXT order's lists (2 x 32 of the own-cluster
-        // list, 4 x 32 of the search list) are requested before the current order is resolved: their L2 latency
-        // hides behind it instead of sitting on the order-to-order chain.
-        uint32_t po0 = DEAD32, po1 = DEAD32, pr0 = DEAD32, pr1 = DEAD32, pr2 = DEAD32, pr3 = DEAD32;
-        auto prefetch = [&](int jn) {
-            const uint32_t pick = __shfl_sync(FULL, pd, jn) & 0xFFFF;
-            const uint32_t *lo = ownl + (size_t)pick * own_pitch + lane, *lr = regl + (size_t)pick * reg_pitch + lane;
-            po0 = __ldg(lo); po1 = own_pitch > 32 ? __ldg(lo + 32) : DEAD32;
-            pr0 = __ldg(lr); pr1 = reg_pitch > 32 ? __ldg(lr + 32) : DEAD32;
-            pr2 = reg_pitch > 64 ? __ldg(lr + 64) : DEAD32; pr3 = reg_pitch > 96 ? __ldg(lr + 96) : DEAD32;
+        // candidate ring: one cp.async group per order, issued two orders ahead
+        unsigned pf = todo; int ps = 0, cs = 0;
+        auto issue = [&]() {
+            if (pf) {
+                const int jn = __ffs(pf) - 1; pf &= pf - 1;
+                const uint32_t pick = __shfl_sync(FULL, pd, jn) & 0xFFFF;
+                const uint32_t *lo = ownl + (size_t)pick * own_pitch + lane, *lr = regl + (size_t)pick * reg_pitch + lane;
+                uint32_t *dst = ring + ps * SN_SLOT_WORDS + lane;
+#pragma unroll
+                for (int u = 0; u < SN_OWN_CH; u++) if (u < own_pf) sn_cp_async4(dst + u * 32, lo + u * 32);
+#pragma unroll
+                for (int u = 0; u < SN_REG_CH; u++) if (u < reg_pf) sn_cp_async4(dst + (SN_OWN_CH + u) * 32, lr + u * 32);
+            }
+            sn_cp_commit();
+            ps = ps == SN_RING - 1 ? 0 : ps + 1;
         };
-        if (todo) prefetch(__ffs(todo) - 1);
+        issue(); issue();
         while (todo) {
             const int j = __ffs(todo) - 1; todo &= todo - 1;
+            if (dbg & 8) { rej++; continue; }
+            issue();
+            const uint32_t *slot = ring + cs * SN_SLOT_WORDS + lane;
+            cs = cs == SN_RING - 1 ? 0 : cs + 1;
             const uint32_t o_pd = __shfl_sync(FULL, pd, j);
             const int o_val = __shfl_sync(FULL, val, j);
             const int c = __shfl_sync(FULL, oc, j);
+            const int Sj = __shfl_sync(FULL, S, j);                           // idle vehicles in the rest of the search list, now
             const uint32_t pick = o_pd & 0xFFFF;
             const int s0 = soff[c];
             const int own = live[c];
-            const uint32_t *lst; int nch, gsz;
-            uint32_t e0, e1, e2, e3;
+            if (own == 0 && Sj == 0) { rej++; rejval += o_val; sn_cp_wait<SN_RING - 1>(); continue; }   // drained since it was classified
+            const uint32_t *lst; int nch, pfn;
             if (own > 0) {                                                    // simulator.py:925-934: the own cluster only
-                lst = ownl + (size_t)pick * own_pitch; nch = own_pitch >> 5; gsz = min(2, nch);
-                e0 = po0; e1 = po1; e2 = DEAD32; e3 = DEAD32;
+                lst = ownl + (size_t)pick * own_pitch; nch = own_pitch >> 5; pfn = own_pf;
                 my_lookups += lane == 0 ? own : 0;
             } else {                                                          // FindServerVehicleFunction (:978-996)
-                lst = regl + (size_t)pick * reg_pitch; nch = reg_pitch >> 5; gsz = min(4, nch);
-                e0 = pr0; e1 = pr1; e2 = pr2; e3 = pr3;
-                const int len = soff[c + 1] - s0;
-                for (int t = 1 + lane; t < len; t += 32) my_lookups += live[sidx[s0 + t]];
+                lst = regl + (size_t)pick * reg_pitch; nch = reg_pitch >> 5; pfn = reg_pf;
+                slot += SN_OWN_CH * 32;
+                my_lookups += lane == 0 ? Sj : 0;
             }
-            if (todo) prefetch(__ffs(todo) - 1);
+            sn_cp_wait<SN_RING - 1>();                                        // this order's group has landed
             // candidates in ascending (cost, search position): the first occupied one wins
             int wnode = -1; uint32_t e0hi = 0;
             for (int ch = 0;;) {
+                // the next (up to) 4 x 32 entries: from the ring while they were requested ahead, else from L2
+                const int gsz = min(4, (ch < pfn ? pfn : nch) - ch);
+                uint32_t e0, e1 = DEAD32, e2 = DEAD32, e3 = DEAD32;
+                if (ch < pfn) {
+                    const uint32_t *q = slot + ch * 32;
+                    e0 = q[0]; if (gsz > 1) e1 = q[32]; if (gsz > 2) e2 = q[64]; if (gsz > 3) e3 = q[96];
+                } else {
+                    const uint32_t *q = lst + ch * 32 + lane;
+                    e0 = __ldg(q); if (gsz > 1) e1 = __ldg(q + 32); if (gsz > 2) e2 = __ldg(q + 64); if (gsz > 3) e3 = __ldg(q + 96);
+                }
                 const bool o0 = e0 != DEAD32 && cnt[e0 & 0xFFFF] != 0, o1 = e1 != DEAD32 && cnt[e1 & 0xFFFF] != 0;
                 const bool o2 = e2 != DEAD32 && cnt[e2 & 0xFFFF] != 0, o3 = e3 != DEAD32 && cnt[e3 & 0xFFFF] != 0;
                 const unsigned m0 = __ballot_sync(FULL, o0), m1 = __ballot_sync(FULL, o1);
                 const unsigned m2 = __ballot_sync(FULL, o2), m3 = __ballot_sync(FULL, o3);
-                if (!(m0 | m1 | m2 | m3)) {                                   // nothing in these entries: the next 4 x 32
+                if (!(m0 | m1 | m2 | m3)) {                                   // nothing in these entries
                     ch += gsz;
-                    const uint32_t last = gsz == 4 ? e3 : gsz == 2 ? e1 : gsz == 1 ? e0 : e2;
+                    const uint32_t last = gsz == 4 ? e3 : gsz == 3 ? e2 : gsz == 2 ? e1 : e0;
                     if (ch >= nch || __shfl_sync(FULL, last, 31) == DEAD32) break;       // padding reached: nothing left
-                    gsz = min(4, nch - ch);
-                    const uint32_t *q = lst + ch * 32 + lane;
-                    e0 = __ldg(q); e1 = gsz > 1 ? __ldg(q + 32) : DEAD32;
-                    e2 = gsz > 2 ? __ldg(q + 64) : DEAD32; e3 = gsz > 3 ? __ldg(q + 96) : DEAD32;
                     continue;
                 }
                 const int u0 = m0 ? 0 : m1 ? 1 : m2 ? 2 : 3;
@@ -423,7 +462,7 @@ match_nodes_kernel(DevParams P, int k, int n_sidx, int tab_ints, int per_warp, i
                 bool cand = (m >> lane & 1) && (e >> 16) == e0hi;             // occupied nodes at the same (cost, position)
                 const unsigned cm = __ballot_sync(FULL, cand);
                 bool cont = __shfl_sync(FULL, e >> 16, 31) == e0hi;           // ... may continue in the next 32 entries
-                if (!(cm & (cm - 1)) && !cont) { wnode = (int)(__shfl_sync(FULL, e, f) & 0xFFFF); break; }
+                if ((!(cm & (cm - 1)) && !cont) || (dbg & 1)) { wnode = (int)(__shfl_sync(FULL, e, f) & 0xFFFF); break; }
                 uint32_t wkey = DEAD32;                                       // several: idle-list order decides (Q5)
                 for (;;) {
                     const uint32_t key = cand ? head_key(e & 0xFFFF) : DEAD32;
@@ -449,16 +488,19 @@ match_nodes_kernel(DevParams P, int k, int n_sidx, int tab_ints, int per_warp, i
             // pop the head of the node's queue (IdleVehicles.remove, :963): the vehicle is `ord` slots before the run end
             unsigned ord = cnt[wnode];
             __syncwarp();                                                     // every lane has read the byte lane 0 rewrites
+            if (dbg & 4) { matches++; continue; }
             if (ord == 255u) {
                 ord = gcnt[wnode];
                 if (lane == 0) { gcnt[wnode] = (uint16_t)(ord - 1); if (ord - 1 < 255u) cnt[wnode] = (uint8_t)(ord - 1); }
             } else if (lane == 0) cnt[wnode] = (uint8_t)(ord - 1);
             if (lane == 0) live[src] = (uint16_t)(live[src] - 1);
+            S -= (myreg[src >> 5] >> (src & 31)) & 1;                         // one vehicle fewer in this lane's search list
             __syncwarp();
             if (lane == j) { my_node = (uint32_t)wnode; my_ord = ord; my_mn = mn; }
             matches++; wait_sum += mn;
         }
-        if (lane < nb_ord) {                                                  // commit the chunk (simulator.py:946-969)
+        sn_cp_wait<0>();
+        if (lane < nb_ord && !(dbg & 2)) {                                    // commit the chunk (simulator.py:946-969)
             uint32_t word = 0x0000FFFFu;                                      // ArriveInfo = "Reject"
             if (my_node != DEAD32) {
                 const uint32_t my_v = sveh[(unsigned)runend[my_node] - my_ord];
