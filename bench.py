@@ -371,7 +371,7 @@ class Runner:
         else:
             names = ("update", "match", "supply")
             fns = lambda k: (lambda: eng.update(k), lambda: eng.match(k), lambda: eng.supply_expect(k))
-            dom, kname = "match", "match_search_kernel"
+            dom, kname = "match", ("match_nodes_kernel" if eng.search_nodes_active else "match_search_kernel")
         evs = {n: [] for n in names}
         eng.reset(self.loc0)
         for k in range(T):

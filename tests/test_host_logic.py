@@ -346,3 +346,29 @@ def test_setup_on_the_shipped_day_matches_reference_inputs():
     assert np.array_equal(sim.city.nb_off, z["in_nb_off"]) and np.array_equal(sim.city.nb_idx, z["in_nb_idx"])
     assert np.array_equal([o.OrderValue for o in sim.Orders], z["in_order_value"])
     assert walls[1] < 15.0
+
+
+def test_search_node_tables_are_the_sorted_candidates():
+    """City.search_node_tables (the static inputs of the node-mode neighbour search): every row holds exactly the
+    nodes of the own cluster / of the rest of the DFS pre-order list, ascending in (cost, position, rank)."""
+    from vehicles_dispatch_simulator_b200.synthetic import synthetic_grid_city
+    city = synthetic_grid_city(side_m=800, service_m=2000, neighbor_can_server=True, n_nodes=500)
+    t = city.search_node_tables()
+    rank, cbase = t["node_rank"], t["cluster_base"]
+    soff, sidx = city.search_lists()
+    order = np.argsort(np.where(rank == 0xFFFF, 1 << 20, rank.astype(np.int64)), kind="stable")[:int(cbase[-1])]
+    assert np.array_equal(rank[order], np.arange(len(order)))                       # rank -> node is a bijection
+    for c in range(city.n_clusters):
+        assert np.array_equal(np.sort(order[cbase[c]:cbase[c + 1]]), np.sort(city.cluster_nodes[c]))
+    rng = np.random.default_rng(0)
+    for p in rng.choice(city.valid_nodes(), 25):
+        c = int(city.node2cluster[p])
+        for tab, clusters in ((t["own_list"], [(0, c)]),
+                              (t["search_list"], [(i + 1, int(s)) for i, s in enumerate(sidx[soff[c] + 1:soff[c + 1]])])):
+            row = tab[p]
+            ent = row[row != 0xFFFFFFFF]
+            assert (np.diff(ent.astype(np.int64)) > 0).all() and (row[len(ent):] == 0xFFFFFFFF).all()
+            assert len(row) % 32 == 0 and len(row) - len(ent) >= 0
+            want = sorted((int(city.cost_u8[p, n]) << 24) | (pos << 16) | int(rank[n])
+                          for pos, cl in clusters for n in city.cluster_nodes[cl])
+            assert ent.tolist() == want
