@@ -192,7 +192,7 @@ int  vds_bind_queues(vds_handle h, uint16_t *q_next, uint16_t *q_tail);
  * and per-replica scratch the library fills every tick (contents meaningful only to the library):
  *   node_count u8[R][ranks_padded], run_end u16[R][ranks_padded], node_count_exact u16[R][ranks_padded],
  *   head_key u32[R][ranks_padded],
- *   slot_vehicle u16[2][R][Vp], slot_key u32[2][R][Vp] (double-buffered: vds_update merges the previous tick's sorted
+ *   slot_vehicle u32[2][R][Vp], slot_key u32[2][R][Vp] (double-buffered: vds_update merges the previous tick's sorted
  *   slots with this tick's arrivals; after vds_reset / vds_bind_state, a fused rollout window or a tick that does not
  *   follow the previous update directly, it sorts from scratch.  A caller that writes the vehicle arrays itself must
  *   call vds_bind_state again before the next vds_update).
@@ -206,7 +206,7 @@ typedef struct vds_search_nodes {
     uint8_t  *node_count;
     uint16_t *run_end;
     uint16_t *node_count_exact;
-    uint16_t *slot_vehicle;
+    uint32_t *slot_vehicle;
     uint32_t *slot_key;
     uint32_t *head_key;
     int32_t   ranks_padded;

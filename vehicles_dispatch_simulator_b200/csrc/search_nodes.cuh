@@ -7,7 +7,7 @@
 //
 //   update_nodes_kernel (CTA per replica)   UpdateFunction (:1006-1024) + order advance (:912-919), and the
 //       replica's idle vehicles sorted by NODE RANK (nodes renumbered cluster by cluster) and, inside a node,
-//       by idle key (== list order):  sveh / skey [2][R][Vp] sorted slots (double-buffered), runend
+//       by idle key (== list order):  sveh (vehicle | rank << 16) / skey [2][R][Vp] sorted slots (double-buffered), runend
 //       u16[R][NP] = end of every node's run, ncnt u8[R][NP] = run length saturated at 255 (exact value in gcnt
 //       then).  The sort is a STABLE MERGE with the previous tick's slots: a vehicle that stays idle keeps its
 //       place relative to the other survivors of its node (one block-wide compaction over the old slots, O(V)),
@@ -47,7 +47,7 @@ static SnLayout sn_layout(int C, int NP, int n_sidx, int warps)
 }
 static int sn_update_smem(int C, int NP, int Vp)
 {
-    return (int)sizeof(int) * (((C + 3) & ~3) + 32 + NP + ((Vp + 31) >> 5) + 8 + ((Vp >> 3) + 3) / 4);
+    return (int)sizeof(int) * (((C + 3) & ~3) + 32 + NP + ((Vp + 31) >> 5) + 16 + ((Vp >> 3) + 3) / 4);
 }
 
 // two block-wide scans over the per-node counters at once: A (new entries) exclusive, S (survivors) inclusive
@@ -97,17 +97,17 @@ update_nodes_kernel(DevParams P, int k, int incremental, int nbuf)
     int *wtot = ocnt + Cp;                                       // [32]
     unsigned *A32 = reinterpret_cast<unsigned *>(wtot + 32);     // [NP/2] u16 pairs: new entries per node -> exclusive scan -> cursor
     unsigned *S32 = A32 + (NP >> 1);                             // [NP/2] u16 pairs: survivors per node -> inclusive scan
-    unsigned *sflag = S32 + (NP >> 1);                           // [(Vp+31)/32 + 8] survivor bit per old slot
-    uint8_t *fresh8 = reinterpret_cast<uint8_t *>(sflag + ((P.Vp + 31) >> 5) + 8);   // [Vp/8] NEW-entry bits per group of 8 vehicles
+    unsigned *sflag = S32 + (NP >> 1);                           // [(Vp+31)/32 + 16] survivor bit per old slot
+    uint8_t *fresh8 = reinterpret_cast<uint8_t *>(sflag + ((P.Vp + 31) >> 5) + 16);   // [Vp/8] NEW-entry bits per group of 8 vehicles
     uint16_t *A = reinterpret_cast<uint16_t *>(A32), *S = reinterpret_cast<uint16_t *>(S32);
     __shared__ int s_arrivals;
 
     const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const size_t vb = (size_t)r * P.Vp;
     const size_t bufstride = (size_t)P.R * P.Vp;
-    const uint16_t *sveh_o = P.SN.sveh + (size_t)(nbuf ^ 1) * bufstride + vb;
+    const uint32_t *sveh_o = P.SN.sveh + (size_t)(nbuf ^ 1) * bufstride + vb;
     const uint32_t *skey_o = P.SN.skey + (size_t)(nbuf ^ 1) * bufstride + vb;
-    uint16_t *sveh_n = P.SN.sveh + (size_t)nbuf * bufstride + vb;
+    uint32_t *sveh_n = P.SN.sveh + (size_t)nbuf * bufstride + vb;
     uint32_t *skey_n = P.SN.skey + (size_t)nbuf * bufstride + vb;
     uint16_t *g_end = P.SN.runend + (size_t)r * NP;
     uint32_t *g_hkey = P.SN.hkey + (size_t)r * NP;               // idle key of the first vehicle of every node's run
@@ -126,17 +126,20 @@ update_nodes_kernel(DevParams P, int k, int incremental, int nbuf)
     const uint16_t *nrank = P.SN.nrank;
 
     // survivors: an old slot whose vehicle is still idle under the same key (it was neither matched nor dispatched)
-    const int SW = ((old_total + UPD_WARPS * 32 - 1) / (UPD_WARPS * 32)) * 32;     // old slots per warp
-    for (int s = 0; s < SW; s += 32) {
-        const int q = w * SW + s + lane;
-        bool flag = false;
-        if (q < old_total) {
-            const int v = sveh_o[q];
-            flag = P.veh_arrive[vb + v] == IDLE16 && P.veh_key[vb + v] == skey_o[q];
-            if (flag) { const unsigned rk = nrank[P.veh_loc[vb + v]]; atomicAdd(&S32[rk >> 1], 1u << ((rk & 1) * 16)); }
-        }
-        const unsigned b = __ballot_sync(FULL, flag);
-        if (lane == 0) sflag[(w * SW + s) >> 5] = b;
+    // (a slot is vehicle | node rank << 16: the vehicle record is only needed for the idle / key test)
+    const int SW = ((old_total + UPD_WARPS * 64 - 1) / (UPD_WARPS * 64)) * 64;     // old slots per warp, two per lane and pass
+    for (int s = 0; s < SW; s += 64) {
+        const int q0 = w * SW + s + lane, q1 = q0 + 32;
+        uint32_t sl0 = 0, sl1 = 0, k0 = 0, k1 = 0;
+        if (q0 < old_total) { sl0 = sveh_o[q0]; k0 = skey_o[q0]; }
+        if (q1 < old_total) { sl1 = sveh_o[q1]; k1 = skey_o[q1]; }
+        bool f0 = false, f1 = false;
+        if (q0 < old_total) f0 = P.veh_arrive[vb + (sl0 & 0xFFFF)] == IDLE16 && P.veh_key[vb + (sl0 & 0xFFFF)] == k0;
+        if (q1 < old_total) f1 = P.veh_arrive[vb + (sl1 & 0xFFFF)] == IDLE16 && P.veh_key[vb + (sl1 & 0xFFFF)] == k1;
+        if (f0) { const unsigned rk = sl0 >> 16; atomicAdd(&S32[rk >> 1], 1u << ((rk & 1) * 16)); }
+        if (f1) { const unsigned rk = sl1 >> 16; atomicAdd(&S32[rk >> 1], 1u << ((rk & 1) * 16)); }
+        const unsigned b0 = __ballot_sync(FULL, f0), b1 = __ballot_sync(FULL, f1);
+        if (lane == 0) { sflag[(w * SW + s) >> 5] = b0; sflag[((w * SW + s) >> 5) + 1] = b1; }
     }
     __syncthreads();
 
@@ -194,12 +197,12 @@ update_nodes_kernel(DevParams P, int k, int incremental, int nbuf)
             const unsigned b = sflag[w0 + s];
             if (b >> lane & 1) {
                 const int q = w * SW + s * 32 + lane;
-                const int v = sveh_o[q];
-                const unsigned rk = nrank[P.veh_loc[vb + v]];
+                const uint32_t sl = sveh_o[q];
+                const unsigned rk = sl >> 16;
                 const int gi = before + __popc(b & lanemask_lt());
                 const int pos = gi + A[rk];
                 const uint32_t key = skey_o[q];
-                sveh_n[pos] = (uint16_t)v; skey_n[pos] = key;
+                sveh_n[pos] = sl; skey_n[pos] = key;
                 if (gi == (rk ? (int)S[rk - 1] : 0)) g_hkey[rk] = key;        // first survivor of its node
             }
             before += __popc(b);
@@ -276,7 +279,7 @@ update_nodes_kernel(DevParams P, int k, int incremental, int nbuf)
             }
             if (idx == a && S[rk] == (rk ? S[rk - 1] : 0)) g_hkey[rk] = e.y;  // no survivor on the node: first new entry leads
             idx += S[rk];
-            sveh_n[idx] = (uint16_t)(e.x & 0xFFFFu);
+            sveh_n[idx] = e.x;                                  // vehicle | node rank << 16, as scattered in pass 2
             skey_n[idx] = e.y;
         }
     }
@@ -350,7 +353,7 @@ match_nodes_kernel(DevParams P, int k, int n_sidx, int tab_ints, int per_warp, i
     const uint32_t *hkey = keep(P.SN.hkey + (size_t)r * NP);
     uint16_t *gcnt = keep(P.SN.gcnt + (size_t)r * NP);
     const uint32_t *skey = keep(P.SN.skey + (size_t)nbuf * P.R * P.Vp + vb);
-    const uint16_t *sveh = P.SN.sveh + (size_t)nbuf * P.R * P.Vp + vb;
+    const uint32_t *sveh = P.SN.sveh + (size_t)nbuf * P.R * P.Vp + vb;
     const uint32_t *ownl = keep(P.SN.own_list), *regl = keep(P.SN.search_list);
     const uint32_t own_pitch = (uint32_t)P.SN.own_pitch, reg_pitch = (uint32_t)P.SN.search_pitch;
     const int own_pf = min(SN_OWN_CH, (int)(own_pitch >> 5)), reg_pf = min(SN_REG_CH, (int)(reg_pitch >> 5));
@@ -503,7 +506,7 @@ match_nodes_kernel(DevParams P, int k, int n_sidx, int tab_ints, int per_warp, i
         if (lane < nb_ord && !(dbg & 2)) {                                    // commit the chunk (simulator.py:946-969)
             uint32_t word = 0x0000FFFFu;                                      // ArriveInfo = "Reject"
             if (my_node != DEAD32) {
-                const uint32_t my_v = sveh[(unsigned)runend[my_node] - my_ord];
+                const uint32_t my_v = sveh[(unsigned)runend[my_node] - my_ord] & 0xFFFF;
                 int d = (int)((((uint32_t)my_mn + (uint32_t)val + (uint32_t)P.period - 1u) * P.period_magic) >> 20); if (d < 1) d = 1;
                 const int dnode = pd >> 16;
                 P.veh_arrive[vb + my_v] = (uint16_t)((k + d) | 0x8000);

@@ -49,7 +49,7 @@ struct NqLayout { int key, arr, node, nxt, tail, icnt, occ, ooff, wl, wl2, q, ac
 // node-mode neighbour search (search_nodes.cuh; vds_bind_search_nodes)
 struct SnParams {
     const uint16_t *nrank; const int *cbase; const uint32_t *own_list, *search_list;
-    uint8_t *ncnt; uint16_t *runend, *gcnt, *sveh; uint32_t *skey, *hkey;
+    uint8_t *ncnt; uint16_t *runend, *gcnt; uint32_t *sveh, *skey, *hkey;
     int NP, own_pitch, search_pitch;
 };
 struct DevParams {

@@ -272,7 +272,7 @@ class DispatchEngine:
                        own_list=t(tabs["own_list"]), search_list=t(tabs["search_list"]),
                        node_count=z((R, NP), torch.uint8), run_end=z((R, NP), torch.uint16),
                        node_count_exact=z((R, NP), torch.uint16),
-                       slot_vehicle=z((2, R, self.Vp), torch.uint16), slot_key=z((2, R, self.Vp), torch.uint32),
+                       slot_vehicle=z((2, R, self.Vp), torch.uint32), slot_key=z((2, R, self.Vp), torch.uint32),
                        head_key=z((R, NP), torch.uint32))
         f = N.SearchNodes(*[self.sn[n].data_ptr() for n in ("node_rank", "cluster_base", "own_list", "search_list",
                                                              "node_count", "run_end", "node_count_exact", "slot_vehicle",
