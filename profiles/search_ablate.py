@@ -1,3 +1,6 @@
+"""Timing ablations of match_nodes_kernel at one tick (state rebuilt from a snapshot before every launch).
+Needs a library built from commit c2 of the round-2 search work (the VDS_SN_DBG knob: bit0 no tie resolution, bit1 no
+commit, bit2 no pops, bit3 skeleton only); the shipped kernel has no such parameter.  Results: profiles/r2_search_nodes_summary.md."""
 import os, sys
 sys.path.insert(0, '/root/repo')
 import bench, torch, numpy as np

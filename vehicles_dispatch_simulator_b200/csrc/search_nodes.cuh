@@ -313,7 +313,7 @@ template <int N> __device__ __forceinline__ void sn_cp_wait() { asm volatile("cp
 
 #define MN_MAX_WARPS 14
 __global__ void __launch_bounds__(MN_MAX_WARPS * 32, 2)
-match_nodes_kernel(DevParams P, int k, int n_sidx, int tab_ints, int per_warp, int nbuf, int dbg)
+match_nodes_kernel(DevParams P, int k, int n_sidx, int tab_ints, int per_warp, int nbuf)
 {
     extern __shared__ int sm[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -411,7 +411,6 @@ match_nodes_kernel(DevParams P, int k, int n_sidx, int tab_ints, int per_warp, i
         issue(); issue();
         while (todo) {
             const int j = __ffs(todo) - 1; todo &= todo - 1;
-            if (dbg & 8) { rej++; continue; }
             issue();
             const uint32_t *slot = ring + cs * SN_SLOT_WORDS + lane;
             cs = cs == SN_RING - 1 ? 0 : cs + 1;
@@ -465,7 +464,7 @@ match_nodes_kernel(DevParams P, int k, int n_sidx, int tab_ints, int per_warp, i
                 bool cand = (m >> lane & 1) && (e >> 16) == e0hi;             // occupied nodes at the same (cost, position)
                 const unsigned cm = __ballot_sync(FULL, cand);
                 bool cont = __shfl_sync(FULL, e >> 16, 31) == e0hi;           // ... may continue in the next 32 entries
-                if ((!(cm & (cm - 1)) && !cont) || (dbg & 1)) { wnode = (int)(__shfl_sync(FULL, e, f) & 0xFFFF); break; }
+                if (!(cm & (cm - 1)) && !cont) { wnode = (int)(__shfl_sync(FULL, e, f) & 0xFFFF); break; }
                 uint32_t wkey = DEAD32;                                       // several: idle-list order decides (Q5)
                 for (;;) {
                     const uint32_t key = cand ? head_key(e & 0xFFFF) : DEAD32;
@@ -491,7 +490,6 @@ match_nodes_kernel(DevParams P, int k, int n_sidx, int tab_ints, int per_warp, i
             // pop the head of the node's queue (IdleVehicles.remove, :963): the vehicle is `ord` slots before the run end
             unsigned ord = cnt[wnode];
             __syncwarp();                                                     // every lane has read the byte lane 0 rewrites
-            if (dbg & 4) { matches++; continue; }
             if (ord == 255u) {
                 ord = gcnt[wnode];
                 if (lane == 0) { gcnt[wnode] = (uint16_t)(ord - 1); if (ord - 1 < 255u) cnt[wnode] = (uint8_t)(ord - 1); }
@@ -503,7 +501,7 @@ match_nodes_kernel(DevParams P, int k, int n_sidx, int tab_ints, int per_warp, i
             matches++; wait_sum += mn;
         }
         sn_cp_wait<0>();
-        if (lane < nb_ord && !(dbg & 2)) {                                    // commit the chunk (simulator.py:946-969)
+        if (lane < nb_ord) {                                                  // commit the chunk (simulator.py:946-969)
             uint32_t word = 0x0000FFFFu;                                      // ArriveInfo = "Reject"
             if (my_node != DEAD32) {
                 const uint32_t my_v = sveh[(unsigned)runend[my_node] - my_ord] & 0xFFFF;

@@ -1425,8 +1425,7 @@ int vds_match(vds_handle h, int tick, void *stream)
             return fail(h, VDS_ERR_INVALID, "vds_match: vds_update of the same tick must precede it (node-mode neighbour search)");
         const int wp = h->sn_warps, grid = (P.R + wp - 1) / wp;
         cudaStream_t st = (cudaStream_t)stream;
-        int dbg = 0; { const char *e = getenv("VDS_SN_DBG"); if (e) dbg = atoi(e); }      // developer knob (timing ablations)
-        match_nodes_kernel<<<grid, wp * 32, h->sn_smem, st>>>(P, tick, h->n_sidx, h->sn_tab_ints, h->sn_per_warp, h->sn_buf, dbg);
+        match_nodes_kernel<<<grid, wp * 32, h->sn_smem, st>>>(P, tick, h->n_sidx, h->sn_tab_ints, h->sn_per_warp, h->sn_buf);
         CKL("match_nodes_kernel");
     } else {
         const int per_cta = MS_WARPS * (3 * P.C + 2 + 96);
