@@ -297,7 +297,10 @@ __device__ __forceinline__ RollPick roll_search_pick(const uint32_t *ent, const 
     return r;
 }
 
-template <int THREADS, int MINB, bool SEARCH, bool POLICY>
+// TMA: window-start / window-end vehicle table copies as bulk async copies.  A template parameter, not a run-time flag: the
+// shared-memory addresses the window-end stores need stay live across the tick loop and cost the 72-register variants
+// 1.3 % per tick (profiles/r2_tma_experiment.md), so only short windows (where the copies matter) use the TMA variant.
+template <int THREADS, int MINB, bool SEARCH, bool POLICY, bool TMA = false>
 __global__ void __launch_bounds__(THREADS, MINB)
 rollout_local_kernel(DevParams P, int k0, int nticks, RollPolicy pol)
 {
@@ -335,7 +338,7 @@ rollout_local_kernel(DevParams P, int k0, int nticks, RollPolicy pol)
 
     // ---- window start: HBM vehicle table -> shared memory
     __shared__ __align__(8) unsigned long long tma_mbar;
-    if (P.tma) {
+    if (TMA) {
         // five bulk async copies (TMA) issued by one thread, 12 B per vehicle; LocationNode lands in node[], DeliveryPoint
         // in the (still unused) idle-slot pool, then one shared-memory pass keeps the one that applies
         const uint32_t mbar_sa = (uint32_t)__cvta_generic_to_shared(&tma_mbar);
@@ -922,7 +925,7 @@ rollout_local_kernel(DevParams P, int k0, int nticks, RollPolicy pol)
         uint4 *g_dst = reinterpret_cast<uint4 *>(P.veh_dest + vb);
         uint4 *g_clu = reinterpret_cast<uint4 *>(P.veh_cluster + vb);
         uint4 *g_key = reinterpret_cast<uint4 *>(P.veh_key + vb);
-        if (P.tma) {
+        if (TMA) {
             // arrive / cluster / key go back as they are: three bulk async stores (TMA) from shared memory.  (The
             // shared-memory writes of the last tick are made visible to the async proxy first.)
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -946,7 +949,7 @@ rollout_local_kernel(DevParams P, int k0, int nticks, RollPolicy pol)
                 d.h[j] = (idle || pad) ? (uint16_t)IDLE16 : n.h[j];
             }
             g_loc[g] = l.v; g_dst[g] = d.v;
-            if (!P.tma) {
+            if (!TMA) {
                 g_arr[g] = a.v;
                 g_clu[g] = reinterpret_cast<uint4 *>(clus)[g];
                 g_key[2 * g] = reinterpret_cast<uint4 *>(key)[2 * g];

@@ -35,6 +35,7 @@
 
 #define IDLE16 0xFFFFu
 #define VDS_TMA_DEFAULT 1          // measured: profiles/r2_tma_experiment.md (VDS_TMA=0 selects the LDG->STS loops)
+#define VDS_TMA_MAX_TICKS 4        // windows up to this many ticks run the TMA variant of rollout_local_kernel
 #define DEAD32 0xFFFFFFFFu
 #define FULL 0xFFFFFFFFu
 #define UPD_THREADS 256
@@ -1164,6 +1165,10 @@ int vds_create(const vds_config *cfg, vds_handle *out)
         CK(cudaFuncSetAttribute(rollout_local_kernel<512, 1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
         CK(cudaFuncSetAttribute(rollout_local_kernel<1024, 1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
         CK(cudaFuncSetAttribute(rollout_local_kernel<1024, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
+        CK(cudaFuncSetAttribute(rollout_local_kernel<128, 7, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
+        CK(cudaFuncSetAttribute(rollout_local_kernel<256, 3, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
+        CK(cudaFuncSetAttribute(rollout_local_kernel<512, 1, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
+        CK(cudaFuncSetAttribute(rollout_local_kernel<1024, 1, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
         CK(cudaFuncSetAttribute(rollout_local_kernel<128, 7, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
         CK(cudaFuncSetAttribute(rollout_local_kernel<256, 3, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
         CK(cudaFuncSetAttribute(rollout_local_kernel<512, 1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem));
@@ -1538,7 +1543,12 @@ int vds_rollout(vds_handle h, int tick0, int nticks, void *stream)
         h->sn_valid = false;
         cudaStream_t st = (cudaStream_t)stream;
         if (local_mode(h)) {
-            switch (h->roll_threads) {
+            if (h->P.tma && nticks <= VDS_TMA_MAX_TICKS) switch (h->roll_threads) {    // short window: the table copies are a visible share
+            case 128: rollout_local_kernel<128, 7, false, false, true><<<h->P.R, 128, h->roll_smem, st>>>(h->P, tick0, nticks, RollPolicy()); break;
+            case 256: rollout_local_kernel<256, 3, false, false, true><<<h->P.R, 256, h->roll_smem, st>>>(h->P, tick0, nticks, RollPolicy()); break;
+            case 1024: rollout_local_kernel<1024, 1, false, false, true><<<h->P.R, 1024, h->roll_smem, st>>>(h->P, tick0, nticks, RollPolicy()); break;
+            default:  rollout_local_kernel<512, 1, false, false, true><<<h->P.R, 512, h->roll_smem, st>>>(h->P, tick0, nticks, RollPolicy()); break;
+            } else switch (h->roll_threads) {
             case 128: rollout_local_kernel<128, 7, false, false><<<h->P.R, 128, h->roll_smem, st>>>(h->P, tick0, nticks, RollPolicy()); break;
             case 256: rollout_local_kernel<256, 3, false, false><<<h->P.R, 256, h->roll_smem, st>>>(h->P, tick0, nticks, RollPolicy()); break;
             case 1024: rollout_local_kernel<1024, 1, false, false><<<h->P.R, 1024, h->roll_smem, st>>>(h->P, tick0, nticks, RollPolicy()); break;
