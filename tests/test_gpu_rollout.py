@@ -40,6 +40,8 @@ def _engine(city, V, minute, pickup, delivery, R=1, period=10, **kw):
     (600, 6000, [1, 1, 3, 0]),         # window boundaries incl. single fused ticks
     (2500, 4000, None),                # Vp > 2048, idle lists > 32 (general scan path), 256-thread CTAs
     (9000, 5000, None),                # one replica = 126 KB of shared memory: one per SM, 1024-thread CTAs
+    (2500, 3000, [2, 4, 5, 0]),        # 256-thread CTAs: windows on both sides of VDS_TMA_MAX_TICKS (TMA / register-path variant)
+    (9000, 3000, [3, 0]),              # 1024-thread CTAs: a TMA window, then the register-path variant
 ])
 def test_fused_rollout_vs_oracle(cuda_device, V, n_orders, windows):
     rng = np.random.default_rng(V)
