@@ -434,7 +434,38 @@ match_nodes_kernel(DevParams P, int k, int n_sidx, int tab_ints, int per_warp, i
             sn_cp_wait<SN_RING - 1>();                                        // this order's group has landed
             // candidates in ascending (cost, search position): the first occupied one wins
             int wnode = -1; uint32_t e0hi = 0;
-            for (int ch = 0;;) {
+            // the winner among the occupied entries `m` of the 32-entry group `e` (group index ch): the first one, unless
+            // several occupied nodes share its (cost, position) -- then the idle-list order of their heads decides (Q5)
+            auto resolve = [&](uint32_t e, unsigned m, int ch) {
+                const int f = __ffs(m) - 1;
+                e0hi = __shfl_sync(FULL, e >> 16, f);
+                bool cand = (m >> lane & 1) && (e >> 16) == e0hi;             // occupied nodes at the same (cost, position)
+                const unsigned cm = __ballot_sync(FULL, cand);
+                bool cont = __shfl_sync(FULL, e >> 16, 31) == e0hi;           // ... may continue in the next 32 entries
+                if (!(cm & (cm - 1)) && !cont) { wnode = (int)(__shfl_sync(FULL, e, f) & 0xFFFF); return; }
+                uint32_t wkey = DEAD32;
+                for (;;) {
+                    const uint32_t key = cand ? head_key(e & 0xFFFF) : DEAD32;
+                    const uint32_t kmin = __reduce_min_sync(FULL, key);
+                    if (kmin < wkey) {
+                        wkey = kmin;
+                        wnode = (int)(__shfl_sync(FULL, e, __ffs(__ballot_sync(FULL, key == kmin)) - 1) & 0xFFFF);
+                    }
+                    if (!cont || ++ch >= nch) break;
+                    e = __ldg(lst + ch * 32 + lane);
+                    cand = e != DEAD32 && cnt[e & 0xFFFF] != 0 && (e >> 16) == e0hi;
+                    cont = __shfl_sync(FULL, e >> 16, 31) == e0hi;
+                }
+            };
+            int ch = 0;
+            {   // the first group alone: most orders end here, without touching the other requested groups
+                const uint32_t e0 = slot[0];
+                const unsigned m0 = __ballot_sync(FULL, e0 != DEAD32 && cnt[e0 & 0xFFFF] != 0);
+                if (m0) resolve(e0, m0, 0);
+                else if (nch > 1 && __shfl_sync(FULL, e0, 31) != DEAD32) ch = 1;
+                else ch = nch;
+            }
+            while (wnode < 0 && ch < nch) {
                 // the next (up to) 4 x 32 entries: from the ring while they were requested ahead, else from L2
                 const int gsz = min(4, (ch < pfn ? pfn : nch) - ch);
                 uint32_t e0, e1 = DEAD32, e2 = DEAD32, e3 = DEAD32;
@@ -452,32 +483,11 @@ match_nodes_kernel(DevParams P, int k, int n_sidx, int tab_ints, int per_warp, i
                 if (!(m0 | m1 | m2 | m3)) {                                   // nothing in these entries
                     ch += gsz;
                     const uint32_t last = gsz == 4 ? e3 : gsz == 3 ? e2 : gsz == 2 ? e1 : e0;
-                    if (ch >= nch || __shfl_sync(FULL, last, 31) == DEAD32) break;       // padding reached: nothing left
+                    if (__shfl_sync(FULL, last, 31) == DEAD32) break;         // padding reached: nothing left
                     continue;
                 }
                 const int u0 = m0 ? 0 : m1 ? 1 : m2 ? 2 : 3;
-                uint32_t e = u0 == 0 ? e0 : u0 == 1 ? e1 : u0 == 2 ? e2 : e3;
-                const unsigned m = u0 == 0 ? m0 : u0 == 1 ? m1 : u0 == 2 ? m2 : m3;
-                ch += u0;
-                const int f = __ffs(m) - 1;
-                e0hi = __shfl_sync(FULL, e >> 16, f);
-                bool cand = (m >> lane & 1) && (e >> 16) == e0hi;             // occupied nodes at the same (cost, position)
-                const unsigned cm = __ballot_sync(FULL, cand);
-                bool cont = __shfl_sync(FULL, e >> 16, 31) == e0hi;           // ... may continue in the next 32 entries
-                if (!(cm & (cm - 1)) && !cont) { wnode = (int)(__shfl_sync(FULL, e, f) & 0xFFFF); break; }
-                uint32_t wkey = DEAD32;                                       // several: idle-list order decides (Q5)
-                for (;;) {
-                    const uint32_t key = cand ? head_key(e & 0xFFFF) : DEAD32;
-                    const uint32_t kmin = __reduce_min_sync(FULL, key);
-                    if (kmin < wkey) {
-                        wkey = kmin;
-                        wnode = (int)(__shfl_sync(FULL, e, __ffs(__ballot_sync(FULL, key == kmin)) - 1) & 0xFFFF);
-                    }
-                    if (!cont || ++ch >= nch) break;
-                    e = __ldg(lst + ch * 32 + lane);
-                    cand = e != DEAD32 && cnt[e & 0xFFFF] != 0 && (e >> 16) == e0hi;
-                    cont = __shfl_sync(FULL, e >> 16, 31) == e0hi;
-                }
+                resolve(u0 == 0 ? e0 : u0 == 1 ? e1 : u0 == 2 ? e2 : e3, u0 == 0 ? m0 : u0 == 1 ? m1 : u0 == 2 ? m2 : m3, ch + u0);
                 break;
             }
             const uint32_t mn = e0hi >> 8;
