@@ -36,7 +36,7 @@ struct SnLayout { int tab_ints, per_warp, total; };
 #define SN_OWN_CH 2            // 32-entry groups of the own-cluster list / of the search list requested ahead per order
 #define SN_REG_CH 4
 #define SN_RING 3              // orders in flight: the current one and the next two
-#define SN_SLOT_WORDS ((SN_OWN_CH + SN_REG_CH) * 32)
+#define SN_SLOT_WORDS ((SN_OWN_CH > SN_REG_CH ? SN_OWN_CH : SN_REG_CH) * 32)     // a ring slot holds the groups of ONE of the two lists
 static SnLayout sn_layout(int C, int NP, int n_sidx, int warps)
 {
     SnLayout L;
@@ -394,16 +394,26 @@ match_nodes_kernel(DevParams P, int k, int n_sidx, int tab_ints, int per_warp, i
         uint32_t my_node = DEAD32, my_ord = 0, my_mn = 0;       // outcome of order base + lane ("Reject" until matched)
         // candidate ring: one cp.async group per order, issued two orders ahead
         unsigned pf = todo; int ps = 0, cs = 0;
+        unsigned pfreg = 0;                                     // bit s: ring slot s holds search-list groups (else own-cluster groups)
         auto issue = [&]() {
             if (pf) {
                 const int jn = __ffs(pf) - 1; pf &= pf - 1;
                 const uint32_t pick = __shfl_sync(FULL, pd, jn) & 0xFFFF;
-                const uint32_t *lo = ownl + (size_t)pick * own_pitch + lane, *lr = regl + (size_t)pick * reg_pitch + lane;
+                // an own cluster that is empty now is empty at the order's turn: request the search list; otherwise the
+                // own list (should the cluster run empty in the two orders between, the search list is read from L2)
+                const bool regm = live[__shfl_sync(FULL, oc, jn)] == 0;
                 uint32_t *dst = ring + ps * SN_SLOT_WORDS + lane;
+                if (regm) {
+                    const uint32_t *lr = regl + (size_t)pick * reg_pitch + lane;
 #pragma unroll
-                for (int u = 0; u < SN_OWN_CH; u++) if (u < own_pf) sn_cp_async4(dst + u * 32, lo + u * 32);
+                    for (int u = 0; u < SN_REG_CH; u++) if (u < reg_pf) sn_cp_async4(dst + u * 32, lr + u * 32);
+                    pfreg |= 1u << ps;
+                } else {
+                    const uint32_t *lo = ownl + (size_t)pick * own_pitch + lane;
 #pragma unroll
-                for (int u = 0; u < SN_REG_CH; u++) if (u < reg_pf) sn_cp_async4(dst + (SN_OWN_CH + u) * 32, lr + u * 32);
+                    for (int u = 0; u < SN_OWN_CH; u++) if (u < own_pf) sn_cp_async4(dst + u * 32, lo + u * 32);
+                    pfreg &= ~(1u << ps);
+                }
             }
             sn_cp_commit();
             ps = ps == SN_RING - 1 ? 0 : ps + 1;
@@ -413,6 +423,7 @@ match_nodes_kernel(DevParams P, int k, int n_sidx, int tab_ints, int per_warp, i
             const int j = __ffs(todo) - 1; todo &= todo - 1;
             issue();
             const uint32_t *slot = ring + cs * SN_SLOT_WORDS + lane;
+            const bool slot_reg = pfreg >> cs & 1;
             cs = cs == SN_RING - 1 ? 0 : cs + 1;
             const uint32_t o_pd = __shfl_sync(FULL, pd, j);
             const int o_val = __shfl_sync(FULL, val, j);
@@ -424,11 +435,10 @@ match_nodes_kernel(DevParams P, int k, int n_sidx, int tab_ints, int per_warp, i
             if (own == 0 && Sj == 0) { rej++; rejval += o_val; sn_cp_wait<SN_RING - 1>(); continue; }   // drained since it was classified
             const uint32_t *lst; int nch, pfn;
             if (own > 0) {                                                    // simulator.py:925-934: the own cluster only
-                lst = ownl + (size_t)pick * own_pitch; nch = own_pitch >> 5; pfn = own_pf;
+                lst = ownl + (size_t)pick * own_pitch; nch = own_pitch >> 5; pfn = slot_reg ? 0 : own_pf;
                 my_lookups += lane == 0 ? own : 0;
             } else {                                                          // FindServerVehicleFunction (:978-996)
-                lst = regl + (size_t)pick * reg_pitch; nch = reg_pitch >> 5; pfn = reg_pf;
-                slot += SN_OWN_CH * 32;
+                lst = regl + (size_t)pick * reg_pitch; nch = reg_pitch >> 5; pfn = slot_reg ? reg_pf : 0;
                 my_lookups += lane == 0 ? Sj : 0;
             }
             sn_cp_wait<SN_RING - 1>();                                        // this order's group has landed
@@ -459,7 +469,7 @@ match_nodes_kernel(DevParams P, int k, int n_sidx, int tab_ints, int per_warp, i
             };
             int ch = 0;
             {   // the first group alone: most orders end here, without touching the other requested groups
-                const uint32_t e0 = slot[0];
+                const uint32_t e0 = pfn ? slot[0] : __ldg(lst + lane);
                 const unsigned m0 = __ballot_sync(FULL, e0 != DEAD32 && cnt[e0 & 0xFFFF] != 0);
                 if (m0) resolve(e0, m0, 0);
                 else if (nch > 1 && __shfl_sync(FULL, e0, 31) != DEAD32) ch = 1;
