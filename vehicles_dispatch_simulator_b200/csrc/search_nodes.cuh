@@ -547,256 +547,3 @@ match_nodes_kernel(DevParams P, int k, int n_sidx, int tab_ints, int per_warp, i
         st[VDS_STAT_MATCHES] += matches; st[VDS_STAT_WAIT_TIME] += wait_sum; st[VDS_STAT_LOOKUPS] += lk;
     }
 }
-
-// ----------------------------------------------------------------------------- match (node mode, speculative chunks)
-// match_nodes_spec_kernel: the same contract as match_nodes_kernel, but the 32 orders of a chunk are resolved in ROUNDS.
-// In a round every pending order is decided against the state at the start of the round (its scans are independent of
-// one another: their candidate groups are fetched together, no order waits for the pop of the one before); then the
-// longest prefix of the chunk whose decisions still hold when the pops ahead of them are applied in order is committed
-// at once, and the rest goes into the next round.  Inside a tick the idle sets only shrink, so an order's decision
-// (first occupied entry of its list) is overturned by the orders ahead of it in exactly two cases:
-//   (a) they empty its winner node: kth >= vehicles on the node, kth = earlier orders of the round popping that node;
-//   (b) it won a tie on (cost, position) by the head's idle key and an earlier order pops that head (kth > 0) --
-//       pops of the OTHER tied nodes only raise their head keys and leave the winner in place.
-// Everything else an order consulted is monotone: entries ahead of the winner stay empty, an own cluster that still has
-// its winner vehicle is not empty, an empty own cluster stays empty, "nothing in reach" stays so.  A not-committed order
-// resumes its scan at the 32-entry group of its first occupied entry (restarts when its own cluster ran empty meanwhile
-// and it moves on to the search list).  profiles/spec_model.py replays the rule on the CPU: ~2.5 rounds per 32-order
-// chunk on config 3 instead of ~19 sequential order steps.
-#define SN_STAGE 16            // orders whose next candidate group is staged per pass
-static SnLayout sn_spec_layout(int C, int NP, int n_sidx, int warps)
-{
-    SnLayout L;
-    L.tab_ints = ((C + 1) + ((n_sidx + 1) >> 1) + C * ((C + 31) >> 5) + 3) & ~3;   // soff, sidx, search-list membership bitmaps
-    L.per_warp = (NP + 2 * C + 4 * SN_STAGE * 32 + 15) & ~15;                      // cnt u8[NP], live u16[C], staged candidate groups
-    L.total = L.tab_ints * 4 + warps * L.per_warp;
-    return L;
-}
-
-__global__ void __launch_bounds__(MN_MAX_WARPS * 32, 2)
-match_nodes_spec_kernel(DevParams P, int k, int n_sidx, int tab_ints, int per_warp, int nbuf)
-{
-    extern __shared__ int sm[];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int C = P.C, NP = P.SN.NP, RW = (C + 31) >> 5;
-    int *soff = sm;
-    uint16_t *sidx = reinterpret_cast<uint16_t *>(soff + (C + 1));
-    unsigned *regmask = reinterpret_cast<unsigned *>(soff + (C + 1) + ((n_sidx + 1) >> 1));   // [C][RW] bit s of row c: s is in c's search list at a position >= 1
-    for (int i = threadIdx.x; i <= C; i += blockDim.x) soff[i] = P.soff[i];
-    for (int i = threadIdx.x; i < n_sidx; i += blockDim.x) sidx[i] = P.sidx[i];
-    for (int i = threadIdx.x; i < C * RW; i += blockDim.x) regmask[i] = 0;
-    __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x)
-        for (int q = soff[c] + 1; q < soff[c + 1]; q++) { const int x = sidx[q]; regmask[c * RW + (x >> 5)] |= 1u << (x & 31); }
-    __syncthreads();
-    const int r = blockIdx.x * (blockDim.x >> 5) + w;
-    if (r >= P.R) return;
-    uint8_t *cnt = reinterpret_cast<uint8_t *>(sm + tab_ints) + (size_t)w * per_warp;    // [NP] idle vehicles standing on the node
-    uint16_t *live = reinterpret_cast<uint16_t *>(cnt + NP);                             // [C] len(IdleVehicles)
-    uint32_t *stage = reinterpret_cast<uint32_t *>(cnt + NP + 2 * C + ((4 - ((NP + 2 * C) & 3)) & 3));   // [SN_STAGE][32]
-    const unsigned stage_s = (unsigned)__cvta_generic_to_shared(stage);
-    const uint8_t *cnt0 = keep(P.SN.ncnt + (size_t)r * NP);                              // the same counts at the start of the tick
-    {
-        const uint4 *g = reinterpret_cast<const uint4 *>(cnt0);
-        uint4 *s = reinterpret_cast<uint4 *>(cnt);
-        for (int i = lane; i < (NP >> 4); i += 32) s[i] = g[i];
-        const int *g_lv = P.idle_live + (size_t)r * C;
-        for (int i = lane; i < C; i += 32) live[i] = (uint16_t)g_lv[i];
-    }
-    __syncwarp();
-    const int ro = P.OR == 1 ? 0 : r;
-    const int *toff = P.toff + (size_t)ro * (P.T + 1);
-    const int tb = toff[k], n = toff[k + 1] - tb;
-    const uint32_t *opd = P.opd + (size_t)ro * P.Nmax + tb;
-    const uint8_t *oval = P.oval + (size_t)ro * P.Nmax + tb;
-    uint32_t *res = keep(P.order_res + (size_t)r * P.Nmax + tb);
-    const size_t vb = (size_t)r * P.Vp;
-    const uint16_t *runend = keep(P.SN.runend + (size_t)r * NP);
-    const uint32_t *hkey = keep(P.SN.hkey + (size_t)r * NP);
-    uint16_t *gcnt = keep(P.SN.gcnt + (size_t)r * NP);
-    const uint32_t *skey = keep(P.SN.skey + (size_t)nbuf * P.R * P.Vp + vb);
-    const uint32_t *sveh = P.SN.sveh + (size_t)nbuf * P.R * P.Vp + vb;
-    const uint32_t *ownl = keep(P.SN.own_list), *regl = keep(P.SN.search_list);
-    const uint32_t own_pitch = (uint32_t)P.SN.own_pitch, reg_pitch = (uint32_t)P.SN.search_pitch;
-    const uint32_t thr = P.threshold > 255 ? 255u : (P.threshold < 0 ? 0u : (uint32_t)P.threshold);
-    const bool never = P.threshold < 0;
-    const unsigned lt = lanemask_lt();
-
-    int rej = 0, rejval = 0, matches = 0, wait_sum = 0, lookups = 0;        // per lane, reduced at the end
-
-    // idle key of the head of a node's queue (see match_nodes_kernel)
-    auto head_key = [&](unsigned node) -> uint32_t {
-        unsigned c = cnt[node];
-        const uint32_t h0 = hkey[node]; const unsigned c0 = cnt0[node];
-        if (c == c0 && c != 255u) return h0;
-        if (c == 255u) c = gcnt[node];
-        return skey[(unsigned)runend[node] - c];
-    };
-
-    uint32_t pdn = 0; int valn = 0;                              // the next 32 orders, requested one chunk ahead
-    if (lane < n) { pdn = opd[lane]; valn = oval[lane]; }
-    for (int base = 0; base < n; base += 32) {
-        const uint32_t pd = pdn; const int val = valn;
-        if (base + 32 + lane < n) { pdn = opd[base + 32 + lane]; valn = oval[base + 32 + lane]; }
-        const int nb_ord = min(32, n - base);
-        bool pend = lane < nb_ord;
-        int oc = 0, S = 0, s0 = 0;
-        const unsigned *myreg = regmask;
-        if (pend) {
-            oc = __ldg(P.n2c + (pd & 0xFFFF));
-            s0 = soff[oc];
-            for (int q = s0 + 1; q < soff[oc + 1]; q++) S += live[sidx[q]];          // idle vehicles in the rest of the search list
-            myreg = regmask + oc * RW;
-        }
-        uint32_t my_node = DEAD32, my_ord = 0, my_mn = 0;       // outcome of order base + lane ("Reject" until matched)
-        int mode = -1, gleft = 0;                               // list being scanned (0 own cluster, 1 search list), groups after the current one
-        const uint32_t *mygrp = ownl;                           // the 32-entry group of that list to scan next
-        const uint32_t pick = pd & 0xFFFF;
-
-        while (__any_sync(FULL, pend)) {                        // one round
-            // ---- classify against the state at the start of the round
-            int own_rs = 0;
-            if (pend) {
-                own_rs = live[oc];
-                if (own_rs > 0) {                                                    // simulator.py:925-934: the own cluster only
-                    if (mode != 0) { mode = 0; mygrp = ownl + (size_t)pick * own_pitch; gleft = (int)(own_pitch >> 5) - 1; }
-                } else if (S > 0) {                                                  // FindServerVehicleFunction (:978-996)
-                    if (mode != 1) { mode = 1; mygrp = regl + (size_t)pick * reg_pitch; gleft = (int)(reg_pitch >> 5) - 1; }
-                } else { pend = false; rej++; rejval += val; }                       // nothing idle in reach, now and later
-            }
-            // ---- scan: first occupied entry of every pending order's list, then the occupied entries sharing its
-            // (cost, position).  The scans of a round do not depend on one another: the next 32-entry group of up to
-            // SN_STAGE orders is copied to shared memory by cp.async (all copies in flight together), then each order's
-            // group is tested by the whole warp (one occupancy byte per lane) and the outcome handed to the order's lane.
-            uint32_t win = DEAD32; bool tie = false;                                 // winner entry (cost, position, node); several tied nodes
-            unsigned wmask = __ballot_sync(FULL, pend);
-            while (wmask) {
-                unsigned m = wmask;
-                {
-                    const unsigned long long mg = (unsigned long long)(uintptr_t)mygrp;
-                    unsigned sdst = stage_s + lane * 4;
-                    for (int ns = 0; m && ns < SN_STAGE; ns++, sdst += 128) {
-                        const int j = __ffs(m) - 1; m &= m - 1;
-                        const uint32_t *g = reinterpret_cast<const uint32_t *>((uintptr_t)__shfl_sync(FULL, mg, j));
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(sdst), "l"(g + lane) : "memory");
-                    }
-                }
-                sn_cp_commit(); sn_cp_wait<0>();
-                __syncwarp();
-                const uint32_t *sp = stage + lane;
-                for (unsigned mm = wmask & ~m; mm; sp += 32) {
-                    const int j = __ffs(mm) - 1; mm &= mm - 1;
-                    uint32_t e = *sp;
-                    const bool occ = e != DEAD32 && cnt[e & 0xFFFF] != 0;
-                    const unsigned om = __ballot_sync(FULL, occ);
-                    if (!om) {                                                       // nothing in these 32 entries
-                        const bool last = (lane == 31 && e == DEAD32) || (lane == j && gleft == 0);
-                        if (__any_sync(FULL, last)) wmask &= ~(1u << j);             // padding / end of the row: TempMin == None
-                        else if (lane == j) { mygrp += 32; gleft--; }
-                        continue;
-                    }
-                    wmask &= ~(1u << j);
-                    uint32_t wn = __shfl_sync(FULL, e, __ffs(om) - 1);               // first occupied entry
-                    const unsigned sm_ = __ballot_sync(FULL, (e >> 16) == (wn >> 16));
-                    unsigned cm = sm_ & om;                                          // occupied nodes at the same (cost, position)
-                    bool several = false;
-                    if ((cm & (cm - 1)) || (sm_ >> 31)) {                            // several, or the run may continue in the next group:
-                        const uint32_t e0hi = wn >> 16;                              // idle-list order decides (Q5)
-                        const uint32_t *g = reinterpret_cast<const uint32_t *>((uintptr_t)__shfl_sync(FULL, (unsigned long long)(uintptr_t)mygrp, j));
-                        int left = __shfl_sync(FULL, gleft, j);
-                        bool cand = cm >> lane & 1, cont = sm_ >> 31;
-                        int ncand = __popc(cm);
-                        uint32_t wkey = DEAD32;
-                        for (;;) {
-                            const uint32_t key = cand ? head_key(e & 0xFFFF) : DEAD32;
-                            const uint32_t kmin = __reduce_min_sync(FULL, key);
-                            if (kmin < wkey) {
-                                wkey = kmin;
-                                wn = __shfl_sync(FULL, e, __ffs(__ballot_sync(FULL, key == kmin)) - 1);
-                            }
-                            if (!cont || left-- == 0) break;
-                            g += 32;
-                            e = __ldg(g + lane);
-                            cand = e != DEAD32 && cnt[e & 0xFFFF] != 0 && (e >> 16) == e0hi;
-                            cont = __shfl_sync(FULL, e >> 16, 31) == e0hi;
-                            ncand += __popc(__ballot_sync(FULL, cand));
-                        }
-                        several = ncand > 1;
-                    }
-                    if (lane == j) { win = wn; tie = several; }
-                }
-                __syncwarp();                                                        // stage is rewritten by the next pass
-            }
-            // ---- validate in order: which decisions survive the pops of the lanes ahead
-            const bool dec = pend && win != DEAD32;                                  // has a winner node
-            const bool none = pend && win == DEAD32;                                 // TempMin == None (cannot happen with live > 0)
-            const uint32_t mn = win >> 24, spos = (win >> 16) & 0xFF, bnode = win & 0xFFFF;
-            const bool popper = dec && mn <= thr && !never;                          // else cost > PICKUPTIMEWINDOW (:943): reject
-            unsigned avail = 0;
-            if (dec) { avail = cnt[bnode]; if (avail == 255u) avail = gcnt[bnode]; }
-            const unsigned grp = __match_any_sync(FULL, dec ? bnode : 0x10000u + lane);
-            const unsigned popmask = __ballot_sync(FULL, popper);
-            const unsigned kth = __popc(grp & popmask & lt);
-            const bool bad = dec && (kth >= avail || (popper && tie && kth > 0));
-            const unsigned badmask = __ballot_sync(FULL, bad);
-            const int fb = badmask ? __ffs(badmask) - 1 : 32;
-            const bool commit = (dec || none) && lane < fb;
-            const bool cpop = popper && lane < fb;
-            const unsigned cpopmask = popmask & (fb >= 32 ? FULL : ((1u << fb) - 1u));
-            const int src = spos ? (int)sidx[s0 + spos] : oc;                        // cluster the vehicle comes from
-            __syncwarp();                                                            // every lane has read cnt / live for this round
-            if (cpop) {
-                my_node = bnode; my_ord = avail - kth; my_mn = mn;                   // the vehicle is `ord` slots before the run end
-                matches++; wait_sum += (int)mn;
-                if (kth == 0) {                                                      // first popper of the node writes its new count
-                    const unsigned left = avail - __popc(grp & cpopmask);
-                    if (avail >= 255u) { gcnt[bnode] = (uint16_t)left; if (left < 255u) cnt[bnode] = (uint8_t)left; }
-                    else cnt[bnode] = (uint8_t)left;
-                }
-            }
-            const unsigned cgrp = __match_any_sync(FULL, cpop ? (unsigned)src : 0x10000u + lane);
-            if (cpop && !(cgrp & lt)) live[src] = (uint16_t)(live[src] - __popc(cgrp));
-            // ---- idle vehicles in reach as every order saw them at its turn (lookup counter); S of every lane kept current
-            const int S_rs = S;
-            int dS = 0, dOwn = 0;
-            for (unsigned cm = cpopmask; cm;) {
-                const int i = __ffs(cm) - 1; cm &= cm - 1;
-                const int si = __shfl_sync(FULL, src, i);
-                const int hit = (myreg[si >> 5] >> (si & 31)) & 1;
-                S -= hit;
-                if (i < lane) { dS += hit; dOwn += si == oc; }
-            }
-            if (commit) {
-                lookups += mode == 0 ? own_rs - dOwn : S_rs - dS;
-                if (!cpop) { rej++; rejval += val; }
-                pend = false;
-            }                                                                        // (not committed: mygrp stays at the group of its first occupied entry)
-            __syncwarp();                                                            // the round's pops are visible to every lane
-        }
-        if (lane < nb_ord) {                                                  // commit the chunk (simulator.py:946-969)
-            uint32_t word = 0x0000FFFFu;                                      // ArriveInfo = "Reject"
-            if (my_node != DEAD32) {
-                const uint32_t my_v = sveh[(unsigned)runend[my_node] - my_ord] & 0xFFFF;
-                int d = (int)((((uint32_t)my_mn + (uint32_t)val + (uint32_t)P.period - 1u) * P.period_magic) >> 20); if (d < 1) d = 1;
-                const int dnode = pd >> 16;
-                P.veh_arrive[vb + my_v] = (uint16_t)((k + d) | 0x8000);
-                P.veh_dest[vb + my_v] = (uint16_t)dnode;
-                P.veh_cluster[vb + my_v] = P.n2c[dnode];
-                P.veh_key[vb + my_v] = ((uint32_t)k << 21) | (uint32_t)(base + lane);
-                word = my_v | (my_mn << 16) | ((uint32_t)d << 24);
-            }
-            res[base + lane] = word;
-        }
-    }
-    {
-        int *g_pd = P.per_dispatch + (size_t)r * C, *g_lv = P.idle_live + (size_t)r * C;
-        for (int i = lane; i < C; i += 32) { int l = live[i]; g_pd[i] = l; g_lv[i] = l; }
-    }
-    rej = __reduce_add_sync(FULL, rej); rejval = __reduce_add_sync(FULL, rejval); matches = __reduce_add_sync(FULL, matches);
-    wait_sum = __reduce_add_sync(FULL, wait_sum); lookups = __reduce_add_sync(FULL, lookups);
-    if (lane == 0) {
-        long long *st = P.stats + (size_t)r * VDS_NUM_STATS;
-        st[VDS_STAT_REJECT_NUM] += rej; st[VDS_STAT_SUM_ORDER_VALUE] += rejval;
-        st[VDS_STAT_MATCHES] += matches; st[VDS_STAT_WAIT_TIME] += wait_sum; st[VDS_STAT_LOOKUPS] += lookups;
-    }
-}

@@ -80,7 +80,7 @@ struct vds_handle_s {
     int nq_state;                            // 0 stale (HBM queue links do not describe the vehicle table), 1 fresh reset, 2 valid
     bool nq_off;
     int n_sidx, n_ridx;                      // search-list sizes: decide the shared-memory staging of match_search_kernel
-    bool sn_bound, sn_off, sn_spec; int sn_smem, sn_tab_ints, sn_per_warp, sn_warps;   // node-mode neighbour search (search_nodes.cuh)
+    bool sn_bound, sn_off; int sn_smem, sn_tab_ints, sn_per_warp, sn_warps;   // node-mode neighbour search (search_nodes.cuh)
     bool sn_valid; int sn_buf, sn_last_tick;       // the slot buffer `sn_buf` holds update(sn_last_tick)'s sorted idle vehicles
     char err[512];
     int64_t launches;
@@ -1147,7 +1147,6 @@ int vds_create(const vds_config *cfg, vds_handle *out)
     { const char *e = getenv("VDS_FUSED_SEARCH"); h->fused_search = e && e[0] == '1'; }
     { const char *e = getenv("VDS_NO_NQ"); h->nq_off = e && e[0] == '1'; }
     { const char *e = getenv("VDS_SEARCH_NODES"); h->sn_off = e && e[0] == '0'; }
-    { const char *e = getenv("VDS_SN_SPEC"); h->sn_spec = !(e && e[0] == '0'); }       // 0: the order-by-order match_nodes_kernel
     { const char *e = getenv("VDS_TMA"); P.tma = e ? (e[0] == '1') : VDS_TMA_DEFAULT; }
     P.nodes_pad = vds_padded_nodes(cfg->nodes);
     CK(cudaFuncSetAttribute(match_search_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -1294,8 +1293,8 @@ int vds_bind_search_nodes(vds_handle h, const vds_search_nodes *s)
     const void *ptrs[] = { s->node_rank, s->cluster_base, s->own_list, s->search_list, s->node_count, s->run_end,
                            s->node_count_exact, s->slot_vehicle, s->slot_key, s->head_key };
     for (const void *p : ptrs) if (!p) return fail(h, VDS_ERR_INVALID, "vds_bind_search_nodes: null pointer");
-    if (((uintptr_t)s->node_count | (uintptr_t)s->run_end | (uintptr_t)s->own_list | (uintptr_t)s->search_list) & 15)
-        return fail(h, VDS_ERR_INVALID, "vds_bind_search_nodes: node_count / run_end / own_list / search_list must be 16-byte aligned");
+    if (((uintptr_t)s->node_count | (uintptr_t)s->run_end) & 15)
+        return fail(h, VDS_ERR_INVALID, "vds_bind_search_nodes: node_count / run_end must be 16-byte aligned");
     if (s->ranks_padded < 16 || (s->ranks_padded & 15) || s->ranks_padded > 65520 || s->own_pitch < 32 || (s->own_pitch & 31) ||
         s->search_pitch < 32 || (s->search_pitch & 31))
         return fail(h, VDS_ERR_INVALID, "vds_bind_search_nodes: ranks_padded must be a multiple of 16 (<= 65520), "
@@ -1312,7 +1311,7 @@ int vds_bind_search_nodes(vds_handle h, const vds_search_nodes *s)
     const int upd = sn_update_smem(h->P.C, S.NP, h->P.Vp);
     if (upd > (int)prop.sharedMemPerBlockOptin) return VDS_OK;
     for (int warps = MN_MAX_WARPS; warps >= 1; warps = warps > 7 ? 7 : warps - 1) {
-        const SnLayout L = h->sn_spec ? sn_spec_layout(h->P.C, S.NP, h->n_sidx, warps) : sn_layout(h->P.C, S.NP, h->n_sidx, warps);
+        const SnLayout L = sn_layout(h->P.C, S.NP, h->n_sidx, warps);
         const int per_sm = (MN_MAX_WARPS / warps) < 2 ? 2 : (MN_MAX_WARPS / warps);      // CTAs that should share an SM
         if (L.total > (int)prop.sharedMemPerBlockOptin) continue;
         if (warps > 1 && (size_t)per_sm * (L.total + 1024) > prop.sharedMemPerMultiprocessor) continue;
@@ -1320,8 +1319,7 @@ int vds_bind_search_nodes(vds_handle h, const vds_search_nodes *s)
         break;
     }
     if (h->sn_smem > 0) {
-        if (h->sn_spec) CK(cudaFuncSetAttribute(match_nodes_spec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->sn_smem));
-        else CK(cudaFuncSetAttribute(match_nodes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->sn_smem));
+        CK(cudaFuncSetAttribute(match_nodes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->sn_smem));
         CK(cudaFuncSetAttribute(update_nodes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, upd));
     }
     return VDS_OK;
@@ -1432,8 +1430,7 @@ int vds_match(vds_handle h, int tick, void *stream)
             return fail(h, VDS_ERR_INVALID, "vds_match: vds_update of the same tick must precede it (node-mode neighbour search)");
         const int wp = h->sn_warps, grid = (P.R + wp - 1) / wp;
         cudaStream_t st = (cudaStream_t)stream;
-        if (h->sn_spec) match_nodes_spec_kernel<<<grid, wp * 32, h->sn_smem, st>>>(P, tick, h->n_sidx, h->sn_tab_ints, h->sn_per_warp, h->sn_buf);
-        else match_nodes_kernel<<<grid, wp * 32, h->sn_smem, st>>>(P, tick, h->n_sidx, h->sn_tab_ints, h->sn_per_warp, h->sn_buf);
+        match_nodes_kernel<<<grid, wp * 32, h->sn_smem, st>>>(P, tick, h->n_sidx, h->sn_tab_ints, h->sn_per_warp, h->sn_buf);
         CKL("match_nodes_kernel");
     } else {
         const int per_cta = MS_WARPS * (3 * P.C + 2 + 96);
