@@ -88,7 +88,10 @@ __device__ __forceinline__ void sn_scan_nodes(uint16_t *A, uint16_t *S, int NP, 
 // ------------------------------------------------------------------------------------------ update (node mode)
 // incremental != 0: the `old` slot buffers hold the replica's idle vehicles as sorted by the previous tick's
 // launch of this kernel, and since then vehicles only LEFT the idle set (matches, dispatches).
-__global__ void __launch_bounds__(UPD_THREADS)
+#ifndef UPDN_MINB
+#define UPDN_MINB 6            // CTAs per SM asked of ptxas (40 registers, no spills)
+#endif
+__global__ void __launch_bounds__(UPD_THREADS, UPDN_MINB)
 update_nodes_kernel(DevParams P, int k, int incremental, int nbuf)
 {
     extern __shared__ int sm[];
